@@ -1,0 +1,66 @@
+"""Import the UNMODIFIED reference (read-only, /root/reference/code) for oracle pinning.
+
+Only usable in the build container; the GPU box has no /root/reference.  Follows the recipe
+verified in SURVEY.md Appendix C: stub modules for monai first on sys.path, then the
+reference's ``code`` directory.  Never imports ``networks.net_factory*`` (argv parsing and
+missing modules at import, net_factory_3d.py:3-37).
+"""
+import importlib
+import os
+import sys
+import types
+
+REF_ROOT = os.environ.get("ICL_REFERENCE_ROOT", "/root/reference")
+REF_CODE = os.path.join(REF_ROOT, "code")
+STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
+
+
+def available() -> bool:
+    return os.path.isdir(os.path.join(REF_CODE, "networks"))
+
+
+def _ensure_path():
+    if not available():
+        raise RuntimeError("reference tree not present at %s" % REF_CODE)
+    for p in (REF_CODE, STUBS):
+        if p in sys.path:
+            sys.path.remove(p)
+    sys.path[:0] = [STUBS, REF_CODE]
+    # The product package also has sub-packages called ``networks``/``utils`` *inside*
+    # icl_b200; the reference uses top-level ``networks``/``utils``.  No clash.
+
+
+def load():
+    """Returns a namespace with the reference classes on the hot path."""
+    _ensure_path()
+    ns = types.SimpleNamespace()
+    ns.unet_3D = importlib.import_module("networks.unet_3D").unet_3D
+    m = importlib.import_module("networks.unet_3D_icl")
+    ns.unet_3D_icl = m.unet_3D_icl
+    ns.InherentConsistent = m.InherentConsistent
+    ns.Class_Decoder = m.Class_Decoder
+    ns.Query_Attention = m.Query_Attention
+    ns.SeparableConv3d = m.SeparableConv3d
+    ns.MLP = m.MLP
+    ns.net_utils = importlib.import_module("networks.utils")
+    ns.losses = importlib.import_module("utils.losses")
+    return ns
+
+
+def load_test_single_case():
+    """Reference sliding-window driver test_3D_BraTS.test_single_case (test_3D_BraTS.py:79-142).
+
+    The module imports h5py/medpy/SimpleITK/tqdm/net_factory_3d at top level; none is used by
+    ``test_single_case`` itself, so empty stand-in modules are registered before import.
+    """
+    _ensure_path()
+    for name in ("h5py", "nibabel", "SimpleITK", "medpy", "medpy.metric", "skimage", "skimage.measure",
+                 "networks.net_factory_3d"):
+        if name not in sys.modules:
+            mod = types.ModuleType(name)
+            sys.modules[name] = mod
+    sys.modules["medpy"].metric = sys.modules["medpy.metric"]
+    sys.modules["skimage.measure"].label = None
+    sys.modules["networks.net_factory_3d"].net_factory_3d = None
+    mod = importlib.import_module("test_3D_BraTS")
+    return mod.test_single_case
