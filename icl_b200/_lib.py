@@ -1,0 +1,85 @@
+"""ctypes binding of the C-ABI in include/icl_b200.h (no torch C++ ABI dependency).
+
+The product path has NO fallback: if libicl_b200.so is missing or a call fails, this raises.
+"""
+import ctypes
+import os
+import re
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libicl_b200.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "icl_b200.h")
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "icl_b200: CUDA extension %s not built (run `python -m icl_b200.build`); there is no CPU fallback" % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _lib.icl_last_error.restype = ctypes.c_char_p
+        _lib.icl_launch_count.restype = ctypes.c_ulonglong
+        _declare(_lib)
+    return _lib
+
+
+_CT = {
+    "int": ctypes.c_int, "long long": ctypes.c_longlong, "float": ctypes.c_float, "double": ctypes.c_double,
+    "unsigned long long": ctypes.c_ulonglong,
+}
+
+
+def header_prototypes():
+    """Parse include/icl_b200.h -> {name: [(ctype, argname), ...]} (pointers map to c_void_p)."""
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(int|unsigned long long|const char\*)\s+(icl_\w+)\s*\(([^)]*)\)\s*;", txt):
+        name, args = m.group(2), m.group(3).strip()
+        sig = []
+        if args and args != "void":
+            for a in args.split(","):
+                a = " ".join(a.split())
+                if "*" in a:
+                    sig.append((ctypes.c_void_p, a.split("*")[-1].strip()))
+                else:
+                    parts = a.rsplit(" ", 1)
+                    sig.append((_CT[parts[0].replace("const ", "")], parts[1]))
+        protos[name] = sig
+    return protos
+
+
+def _declare(l):
+    for name, sig in header_prototypes().items():
+        fn = getattr(l, name)
+        fn.argtypes = [t for t, _ in sig]
+        if name not in ("icl_last_error", "icl_launch_count"):
+            fn.restype = ctypes.c_int
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def call(name, *args):
+    """Invoke an int-returning entry point on the current stream; raise on failure."""
+    l = lib()
+    rc = getattr(l, name)(*args, stream())
+    if rc != 0:
+        raise RuntimeError("icl_b200.%s failed (%d): %s" % (name, rc, l.icl_last_error().decode()))
+
+
+def launch_count():
+    return int(lib().icl_launch_count())

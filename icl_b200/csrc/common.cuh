@@ -10,6 +10,8 @@
 // ---- error plumbing: every entry point returns 0 or a negative code; the text is kept here.
 void icl_set_error(const char* fmt, ...);
 int icl_check_launch(const char* what);
+void icl_count_launch(int n);
+#define ICL_LAUNCHED(what) do { icl_count_launch(1); return icl_check_launch(what); } while (0)
 
 #define ICL_REQUIRE(cond, ...)                 \
   do {                                         \
@@ -20,7 +22,7 @@ int icl_check_launch(const char* what);
   } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
-static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+__host__ __device__ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 static inline int grid_for(long long n, int block, int max_blocks = 148 * 16) {
   long long g = (n + block - 1) / block;
   if (g < 1) g = 1;

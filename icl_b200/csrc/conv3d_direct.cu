@@ -1,0 +1,239 @@
+// fp32 CUDA-core 3x3x3 convolution kernels (stride 1, zero padding 1) on F32CL tensors:
+//   * conv3d_direct_fwd : generic forward / data-gradient kernel (any Cin, Cout; two channel-
+//     concatenated sources so UnetUp3_CT's cat([skip, up]) is never materialised).  It serves
+//     the layers the tcgen05 implicit-GEMM kernel does not take (Cin = 1 stem, channel counts
+//     that are not multiples of 16) and is the on-device cross-check for that kernel.
+//   * conv3d_wgrad      : weight (+bias) gradient, fp32 FFMA with register-tiled sliding window.
+// Reference semantics: nn.Conv3d(k=3, s=1, p=1, bias=True), networks/utils.py:104,107.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// weight repacking:  torch [Cout][Cin][27]  ->  fwd  : wp[tap][ci][co]
+//                                              dgrad : wp[26-tap][co][ci]  (flipped, transposed)
+// so that the same kernel computes  out[v][n] = sum_{tap,k} in[v + tap - 1][k] * wp[tap][k][n].
+// ------------------------------------------------------------------------------------------
+__global__ void repack_w_k(const float* __restrict__ w, float* __restrict__ wp, int Cout, int Cin, int dgrad) {
+  const int total = Cout * Cin * 27;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int tap = i % 27, ci = (i / 27) % Cin, co = i / (27 * Cin);
+    if (!dgrad) wp[((long long)tap * Cin + ci) * Cout + co] = w[i];
+    else wp[((long long)(26 - tap) * Cout + co) * Cin + ci] = w[i];
+  }
+}
+ICL_API int icl_repack_w_f32(const float* w, float* wp, int Cout, int Cin, int dgrad, void* stream) {
+  repack_w_k<<<grid_for((long long)Cout * Cin * 27, 256), 256, 0, as_stream(stream)>>>(w, wp, Cout, Cin, dgrad);
+  ICL_LAUNCHED("repack_w_f32");
+}
+
+// ------------------------------------------------------------------------------------------
+// forward.  Block = 256 threads = 2x8x16 output voxels; each thread accumulates NB=16 output
+// channels; K loop over input channels in chunks of 8 staged through shared memory
+// (x halo tile [8][4][10][18] + weights [27][8][16]).
+// ------------------------------------------------------------------------------------------
+#define DT_D 2
+#define DT_H 8
+#define DT_W 16
+#define DT_CI 8
+#define DT_NB 16
+#define DT_HALO ((DT_D + 2) * (DT_H + 2) * (DT_W + 2))
+
+__global__ void __launch_bounds__(256) conv3d_direct_fwd_k(
+    const float* __restrict__ x0, int C0, const float* __restrict__ x1, int C1, const float* __restrict__ wp,
+    const float* __restrict__ bias, float* __restrict__ y, int ldy, int y_coff, double* __restrict__ stats,
+    int B, int D, int H, int W, int Cout) {
+  __shared__ float xs[DT_CI][DT_HALO + 1];
+  __shared__ __align__(16) float ws[27][DT_CI][DT_NB];
+  __shared__ float red[8][2 * DT_NB];
+  const int Cin = C0 + C1;
+  const int tw = (W + DT_W - 1) / DT_W, th = (H + DT_H - 1) / DT_H, td = (D + DT_D - 1) / DT_D;
+  int t = blockIdx.x;
+  const int bw = t % tw; t /= tw;
+  const int bh = t % th; t /= th;
+  const int bd = t % td;
+  const int b = t / td;
+  const int n0 = blockIdx.y * DT_NB;
+  const int tid = threadIdx.x;
+  const int lw = tid % DT_W, lh = (tid / DT_W) % DT_H, ld = tid / (DT_W * DT_H);
+  const int d = bd * DT_D + ld, h = bh * DT_H + lh, w = bw * DT_W + lw;
+  const bool valid = d < D && h < H && w < W;
+
+  float acc[DT_NB];
+#pragma unroll
+  for (int i = 0; i < DT_NB; ++i) acc[i] = 0.f;
+
+  for (int c0 = 0; c0 < Cin; c0 += DT_CI) {
+    __syncthreads();
+    // stage input halo tile (zero outside the volume / beyond Cin)
+    for (int i = tid; i < DT_HALO * DT_CI; i += 256) {
+      const int ci = i % DT_CI, pos = i / DT_CI;
+      const int pw = pos % (DT_W + 2), ph = (pos / (DT_W + 2)) % (DT_H + 2), pd = pos / ((DT_W + 2) * (DT_H + 2));
+      const int gd = bd * DT_D + pd - 1, gh = bh * DT_H + ph - 1, gw = bw * DT_W + pw - 1;
+      const int c = c0 + ci;
+      float v = 0.f;
+      if (c < Cin && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) {
+        const long long vox = (((long long)b * D + gd) * H + gh) * W + gw;
+        v = c < C0 ? x0[vox * C0 + c] : x1[vox * C1 + (c - C0)];
+      }
+      xs[ci][pos] = v;
+    }
+    for (int i = tid; i < 27 * DT_CI * DT_NB; i += 256) {
+      const int n = i % DT_NB, ci = (i / DT_NB) % DT_CI, tap = i / (DT_NB * DT_CI);
+      const int c = c0 + ci, co = n0 + n;
+      ws[tap][ci][n] = (c < Cin && co < Cout) ? wp[((long long)tap * Cin + c) * Cout + co] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int tap = 0; tap < 27; ++tap) {
+      const int kd = tap / 9, kh = (tap / 3) % 3, kw = tap % 3;
+      const int pos = ((ld + kd) * (DT_H + 2) + (lh + kh)) * (DT_W + 2) + lw + kw;
+#pragma unroll
+      for (int ci = 0; ci < DT_CI; ++ci) {
+        const float xv = xs[ci][pos];
+        const float4* wv = reinterpret_cast<const float4*>(&ws[tap][ci][0]);
+#pragma unroll
+        for (int q = 0; q < DT_NB / 4; ++q) {
+          const float4 w4 = wv[q];
+          acc[q * 4 + 0] = fmaf(xv, w4.x, acc[q * 4 + 0]);
+          acc[q * 4 + 1] = fmaf(xv, w4.y, acc[q * 4 + 1]);
+          acc[q * 4 + 2] = fmaf(xv, w4.z, acc[q * 4 + 2]);
+          acc[q * 4 + 3] = fmaf(xv, w4.w, acc[q * 4 + 3]);
+        }
+      }
+    }
+  }
+  // epilogue: bias, store, per-(b, co) sum / sumsq for InstanceNorm
+  const long long vox = (((long long)b * D + d) * H + h) * W + w;
+#pragma unroll
+  for (int n = 0; n < DT_NB; ++n) {
+    const int co = n0 + n;
+    float v = acc[n] + ((bias && co < Cout) ? bias[co] : 0.f);
+    if (!valid || co >= Cout) v = 0.f;
+    else y[vox * ldy + y_coff + co] = v;
+    acc[n] = v;
+  }
+  if (stats) {
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int n = 0; n < DT_NB; ++n) {
+      const float s = warp_sum(acc[n]), q = warp_sum(acc[n] * acc[n]);
+      if (lane == 0) { red[wid][n] = s; red[wid][DT_NB + n] = q; }
+    }
+    __syncthreads();
+    if (tid < 2 * DT_NB) {
+      double tsum = 0.0;
+      for (int k = 0; k < 8; ++k) tsum += (double)red[k][tid];
+      const int n = tid % DT_NB, co = n0 + n;
+      if (co < Cout) atomicAdd(&stats[((long long)b * Cout + co) * 2 + (tid >= DT_NB ? 1 : 0)], tsum);
+    }
+  }
+}
+
+ICL_API int icl_conv3d_direct_fwd(const float* x0, int C0, const float* x1, int C1, const float* wp, const float* bias, float* y,
+                                  int ldy, int y_coff, double* stats, int B, int D, int H, int W, int Cout, void* stream) {
+  ICL_REQUIRE(C0 > 0 && Cout > 0 && (x1 != nullptr || C1 == 0), "conv3d_direct_fwd: bad channel arguments");
+  const long long tiles = (long long)B * cdiv(D, DT_D) * cdiv(H, DT_H) * cdiv(W, DT_W);
+  ICL_REQUIRE(tiles < 2147483647LL, "conv3d_direct_fwd: too many tiles");
+  dim3 grid((unsigned)tiles, cdiv(Cout, DT_NB));
+  conv3d_direct_fwd_k<<<grid, 256, 0, as_stream(stream)>>>(x0, C0, x1, C1, wp, bias, y, ldy, y_coff, stats, B, D, H, W, Cout);
+  ICL_LAUNCHED("conv3d_direct_fwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// weight gradient:  dw[co][ci_off+ci][tap] += sum_{b,v} x[b, v+tap-1, ci] * dy[b, v, co]
+// Block = 128 threads = 8 ci x 16 co pairs, each owning all 27 taps in registers.  The block walks
+// spatial tiles of 4x8x8 voxels (persistent, strided), staging x (halo) and dy through shared
+// memory; along W a 3-wide register window is slid so each new voxel costs 9 x-loads + 1 dy-load
+// for 27 FMAs.  One atomicAdd per (pair, tap) per block at the end.
+// ------------------------------------------------------------------------------------------
+#define WG_D 4
+#define WG_H 8
+#define WG_W 8
+#define WG_CI 8
+#define WG_CO 16
+#define WG_HALO ((WG_D + 2) * (WG_H + 2) * (WG_W + 2))
+#define WG_VOX (WG_D * WG_H * WG_W)
+
+__global__ void __launch_bounds__(128) conv3d_wgrad_k(
+    const float* __restrict__ x, int Cx, const float* __restrict__ dy, int Cout, float* __restrict__ dw, int Cin_total, int ci_off,
+    float* __restrict__ dbias, int B, int D, int H, int W, int tiles_total) {
+  __shared__ float xs[WG_CI][WG_HALO + 1];
+  __shared__ float ds[WG_CO][WG_VOX + 1];
+  const int tid = threadIdx.x;
+  const int ci = tid % WG_CI, co = tid / WG_CI;  // a warp = 8 ci x 4 co
+  const int cib = blockIdx.y % cdiv(Cx, WG_CI), cob = blockIdx.y / cdiv(Cx, WG_CI);
+  const int c_base = cib * WG_CI, n_base = cob * WG_CO;
+  const int tw = cdiv(W, WG_W), th = cdiv(H, WG_H), td = cdiv(D, WG_D);
+  float acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; ++i) acc[i] = 0.f;
+  float bsum = 0.f;
+
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    int t = tile;
+    const int bw = t % tw; t /= tw;
+    const int bh = t % th; t /= th;
+    const int bd = t % td;
+    const int b = t / td;
+    __syncthreads();
+    for (int i = tid; i < WG_HALO * WG_CI; i += 128) {
+      const int cc = i % WG_CI, pos = i / WG_CI;
+      const int pw = pos % (WG_W + 2), ph = (pos / (WG_W + 2)) % (WG_H + 2), pd = pos / ((WG_W + 2) * (WG_H + 2));
+      const int gd = bd * WG_D + pd - 1, gh = bh * WG_H + ph - 1, gw = bw * WG_W + pw - 1;
+      const int c = c_base + cc;
+      float v = 0.f;
+      if (c < Cx && gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W)
+        v = x[((((long long)b * D + gd) * H + gh) * W + gw) * Cx + c];
+      xs[cc][pos] = v;
+    }
+    for (int i = tid; i < WG_VOX * WG_CO; i += 128) {
+      const int n = i % WG_CO, pos = i / WG_CO;
+      const int pw = pos % WG_W, ph = (pos / WG_W) % WG_H, pd = pos / (WG_W * WG_H);
+      const int gd = bd * WG_D + pd, gh = bh * WG_H + ph, gw = bw * WG_W + pw;
+      const int o = n_base + n;
+      float v = 0.f;
+      if (o < Cout && gd < D && gh < H && gw < W) v = dy[((((long long)b * D + gd) * H + gh) * W + gw) * Cout + o];
+      ds[n][pos] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int row = 0; row < WG_D * WG_H; ++row) {
+      const int ld = row / WG_H, lh = row % WG_H;
+      float win[9][3];
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        const int base = ((ld + k / 3) * (WG_H + 2) + (lh + k % 3)) * (WG_W + 2);
+        win[k][0] = 0.f; win[k][1] = xs[ci][base]; win[k][2] = xs[ci][base + 1];
+      }
+#pragma unroll
+      for (int lw = 0; lw < WG_W; ++lw) {
+        const float g = ds[co][row * WG_W + lw];
+        bsum += g;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const int base = ((ld + k / 3) * (WG_H + 2) + (lh + k % 3)) * (WG_W + 2);
+          win[k][0] = win[k][1]; win[k][1] = win[k][2]; win[k][2] = xs[ci][base + lw + 2];
+          acc[k * 3 + 0] = fmaf(win[k][0], g, acc[k * 3 + 0]);
+          acc[k * 3 + 1] = fmaf(win[k][1], g, acc[k * 3 + 1]);
+          acc[k * 3 + 2] = fmaf(win[k][2], g, acc[k * 3 + 2]);
+        }
+      }
+    }
+  }
+  const int c = c_base + ci, o = n_base + co;
+  if (c < Cx && o < Cout) {
+    float* dst = dw + ((long long)o * Cin_total + ci_off + c) * 27;
+#pragma unroll
+    for (int k = 0; k < 27; ++k) atomicAdd(dst + k, acc[k]);
+  }
+  if (dbias && cib == 0 && ci == 0 && o < Cout) atomicAdd(dbias + o, bsum);
+}
+
+ICL_API int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, float* dw, int Cin_total, int ci_off, float* dbias,
+                             int B, int D, int H, int W, void* stream) {
+  const long long tiles = (long long)B * cdiv(D, WG_D) * cdiv(H, WG_H) * cdiv(W, WG_W);
+  ICL_REQUIRE(tiles < 2147483647LL, "conv3d_wgrad: too many tiles");
+  const int gy = cdiv(Cx, WG_CI) * cdiv(Cout, WG_CO);
+  int gx = (int)min(tiles, (long long)max(1, (148 * 8) / gy));
+  conv3d_wgrad_k<<<dim3(gx, gy), 128, 0, as_stream(stream)>>>(x, Cx, dy, Cout, dw, Cin_total, ci_off, dbias, B, D, H, W, (int)tiles);
+  ICL_LAUNCHED("conv3d_wgrad");
+}

@@ -1,0 +1,431 @@
+// 3x3x3 convolution (stride 1, zero pad 1) as an implicit GEMM on the 5th-gen tensor cores:
+// TMA halo-tile loads -> shared memory -> tcgen05.mma (accumulators in TMEM) -> tcgen05.ld
+// epilogue (+bias, fp32 NDHWC store, per-(sample, channel) sum / sum-of-squares for the
+// InstanceNorm that always follows, networks/utils.py:104-109).  The same kernel computes the
+// data gradient (weights packed flipped + transposed).
+//
+// GEMM view per output tile:  D[M=128 voxels][N=NT out-channels] += A[M][K] * B[K][N],
+//   M tile = 16 (h) x 8 (w) voxels of one depth plane; K runs over 3 depth taps x Cin/16 chunks
+//   (one pipeline stage each) x 9 in-plane taps x 16 channels (one MMA each).
+// Operands are bf16.  "parity" mode (P=2) keeps fp32-level accuracy by splitting every operand
+// into hi+lo bf16 planes and issuing hi*hi + hi*lo + lo*hi into the same fp32 accumulator
+// (SURVEY.md §7.3(2)); "fast" mode (P=1) uses the hi plane only.
+//
+// Shared-memory operand layout = UMMA canonical K-major, no swizzle ("interleave"):
+//   A stage  [plane p][k8 chunk j(2)][halo line (18)][halo w (10)][8 ch]   (written by ONE 5-D TMA box per
+//            plane from the PK activation tensor [P][B][C/8][D][H][W][8]); core matrix = 8 consecutive w of
+//            one line (8 x 16 B contiguous), SBO = one halo line (160 B), LBO = one k8 chunk (2880 B).
+//            An in-plane tap (kh,kw) is just a start-address offset of (kh*10 + kw)*16 B, so the 9 taps
+//            reuse one staged tile.
+//   B stage  [plane p][tap 9][k8 chunk 2][n NT][8 ch]  (one 1-D bulk copy; weights pre-packed per stage),
+//            core matrix = 8 n x 16 B, SBO = 128 B, LBO = NT*16 B.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
+#include "common.cuh"
+#include <cuda.h>
+
+#define UM_TH 16
+#define UM_TW 8
+#define UM_HL (UM_TH + 2)
+#define UM_HW (UM_TW + 2)
+#define UM_KC 16
+#define UM_A_PLANE_BYTES (2 * UM_HL * UM_HW * 16)  // 5760: two k8 chunks of one halo plane
+#define UM_A_LBO (UM_HL * UM_HW * 16)              // 2880
+#define UM_A_SBO (UM_HW * 16)                      // 160
+#define UM_MAX_STAGES 8
+#define UM_MAX_COUT 256
+
+struct UmmaConvParams {
+  const __nv_bfloat16* wp;  // packed weights [nt][kd][chunk][p][tap9][2][NT][8]
+  const float* bias;        // [Cout] or null
+  float* y0; int ld0;       // output columns [0, split)
+  float* y1; int ld1;       // output columns [split, Cout)
+  int split;
+  double* stats;            // [B][Cout][2] or null
+  int B, D, H, W;
+  int C0, C1;               // channels of source 0 / source 1 (virtual concat)
+  int Cout, NT, n_tiles;    // N tiling
+  int tiles_h, tiles_w;
+  long long num_tiles;
+  int stages, P;
+  int tmem_cols;
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU box.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("icl conv3d_umma: mbarrier wait timeout (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// smem matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | 1<<46
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct TileCoord { int nt, b, d, h0, w0; };
+__device__ __forceinline__ TileCoord decode_tile(long long t, const UmmaConvParams& p) {
+  TileCoord c;
+  c.nt = (int)(t % p.n_tiles); t /= p.n_tiles;
+  c.w0 = (int)(t % p.tiles_w) * UM_TW; t /= p.tiles_w;
+  c.h0 = (int)(t % p.tiles_h) * UM_TH; t /= p.tiles_h;
+  c.d = (int)(t % p.D);
+  c.b = (int)(t / p.D);
+  return c;
+}
+
+__global__ void __launch_bounds__(192, 1)
+conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const UmmaConvParams p) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t bars[2 * UM_MAX_STAGES + 4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ float sstat[UM_MAX_COUT][2];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int P = p.P, NT = p.NT, stages = p.stages;
+  const uint32_t a_bytes = UM_A_PLANE_BYTES * P;        // per stage
+  const uint32_t b_plane = 9u * NT * 32u;               // per plane per stage
+  const uint32_t b_bytes = b_plane * P;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[UM_MAX_STAGES]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * UM_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * UM_MAX_STAGES + 2]);
+  const int nchunks = (p.C0 + p.C1) / UM_KC;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
+  }
+  for (int i = threadIdx.x; i < UM_MAX_COUT * 2; i += blockDim.x) (&sstat[0][0])[i] = 0.f;
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (warp == 0) {
+    // ================================ TMA producer ================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, p);
+        for (int kd = 0; kd < 3; ++kd) {
+          const int dz = tc.d + kd - 1;
+          if (dz < 0 || dz >= p.D) continue;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
+            const uint32_t sa = smem0 + stage * stage_bytes;
+            const uint32_t fb = full0 + 8 * stage;
+            mbar_expect_tx(fb, stage_bytes);
+            const int k0 = c * UM_KC;
+            const bool src0 = k0 < p.C0;
+            const CUtensorMap* map = src0 ? &mapA0 : &mapA1;
+            const int C8 = (src0 ? p.C0 : p.C1) / 8;
+            const int ch8 = (src0 ? k0 : k0 - p.C0) / 8;
+            for (int pl = 0; pl < P; ++pl)
+              tma_load_5d(sa + pl * UM_A_PLANE_BYTES, map, fb, 0, tc.w0 - 1, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
+            const __nv_bfloat16* wsrc = p.wp + ((((long long)tc.nt * 3 + kd) * nchunks + c) * (long long)(b_bytes / 2));
+            bulk_load(sa + a_bytes, wsrc, b_bytes, fb);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const TileCoord tc = decode_tile(t, p);
+        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, 200 + acc);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NT);
+        uint32_t accumulate = 0;
+        for (int kd = 0; kd < 3; ++kd) {
+          const int dz = tc.d + kd - 1;
+          if (dz < 0 || dz >= p.D) continue;
+          for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(full0 + 8 * stage, phase, 300 + stage);
+            tc_fence_after();
+            const uint32_t sa = smem0 + stage * stage_bytes;
+            const uint32_t sb = sa + a_bytes;
+#pragma unroll
+            for (int t9 = 0; t9 < 9; ++t9) {
+              const uint32_t aoff = (uint32_t)(((t9 / 3) * UM_HW + (t9 % 3)) * 16);
+              const uint64_t a_hi = umma_desc(sa + aoff, UM_A_LBO, UM_A_SBO);
+              const uint64_t b_hi = umma_desc(sb + t9 * (NT * 32), NT * 16, 128);
+              umma_bf16(tmem_d, a_hi, b_hi, idesc, accumulate);
+              accumulate = 1;
+              if (P == 2) {
+                const uint64_t a_lo = umma_desc(sa + UM_A_PLANE_BYTES + aoff, UM_A_LBO, UM_A_SBO);
+                const uint64_t b_lo = umma_desc(sb + b_plane + t9 * (NT * 32), NT * 16, 128);
+                umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
+                umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+              }
+            }
+            umma_commit(empty0 + 8 * stage);
+            if (++stage == stages) { stage = 0; phase ^= 1; }
+          }
+        }
+        umma_commit(tfull0 + 8 * acc);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ================================ epilogue (warps 2..5) ================================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int row = q * 32 + lane;        // accumulator row == voxel within the tile
+    const int hl = row >> 3, wl = row & 7;
+    const int et = threadIdx.x - 64;      // 0..127
+    int acc = 0; uint32_t acc_phase = 0;
+    int cur_b = -1;
+    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const TileCoord tc = decode_tile(t, p);
+      if (p.stats && tc.b != cur_b) {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (cur_b >= 0) {
+          for (int i = et; i < p.Cout * 2; i += 128) {
+            const float v = (&sstat[0][0])[i];
+            if (v != 0.f) atomicAdd(&p.stats[(long long)cur_b * p.Cout * 2 + i], (double)v);
+            (&sstat[0][0])[i] = 0.f;
+          }
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        cur_b = tc.b;
+      }
+      mbar_wait(tfull0 + 8 * acc, acc_phase, 400 + acc);
+      tc_fence_after();
+      const int h = tc.h0 + hl, w = tc.w0 + wl;
+      const bool valid = h < p.H && w < p.W;
+      const long long vox = (((long long)tc.b * p.D + tc.d) * p.H + h) * p.W + w;
+      for (int c0 = 0; c0 < NT; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NT + c0), r);
+        const int n = tc.nt * NT + c0;  // first global output column of this chunk
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? p.bias[n + i] : 0.f);
+        if (valid) {
+          float* dst = (n < p.split) ? p.y0 + vox * p.ld0 + n : p.y1 + vox * p.ld1 + (n - p.split);
+#pragma unroll
+          for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
+        if (p.stats) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float x = valid ? v[i] : 0.f;
+            const float s = warp_sum(x), s2 = warp_sum(x * x);
+            if (lane == 0) { atomicAdd(&sstat[n + i][0], s); atomicAdd(&sstat[n + i][1], s2); }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.stats) {
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (cur_b >= 0)
+        for (int i = et; i < p.Cout * 2; i += 128) {
+          const float v = (&sstat[0][0])[i];
+          if (v != 0.f) atomicAdd(&p.stats[(long long)cur_b * p.Cout * 2 + i], (double)v);
+        }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// weight packing: torch fp32 [Cout][Cin][27] -> bf16 [nt][kd][chunk][p][tap9][half][NT][8]
+//   fwd   : B[n = co][k = ci] for tap (kd,kh,kw)
+//   dgrad : B[n = ci][k = co] for the flipped tap (2-kd, 2-kh, 2-kw)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_w_umma_k(const float* __restrict__ w, __nv_bfloat16* __restrict__ wp, int Cout, int Cin, int dgrad, int NT, int P) {
+  const int Nn = dgrad ? Cin : Cout, Kk = dgrad ? Cout : Cin;
+  const int nchunks = Kk / 16, n_tiles = Nn / NT;
+  const long long total = (long long)Nn * Kk * 27;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int e = (int)(r % 8); r /= 8;
+    const int nl = (int)(r % NT); r /= NT;
+    const int half = (int)(r % 2); r /= 2;
+    const int t9 = (int)(r % 9); r /= 9;
+    const int c = (int)(r % nchunks); r /= nchunks;
+    const int kd = (int)(r % 3); r /= 3;
+    const int nt = (int)r;
+    const int n = nt * NT + nl, k = c * 16 + half * 8 + e;
+    const int tap = kd * 9 + t9;
+    const float v = dgrad ? w[((long long)k * Cin + n) * 27 + (26 - tap)] : w[((long long)n * Cin + k) * 27 + tap];
+    __nv_bfloat16 hi, lo;
+    split_bf16(v, hi, lo);
+    // destination index with the plane dimension inserted after `chunk`
+    const long long stage = ((long long)nt * 3 + kd) * nchunks + c;
+    const long long in_plane = (((long long)t9 * 2 + half) * NT + nl) * 8 + e;
+    const long long plane_sz = 9LL * 2 * NT * 8;
+    wp[(stage * P + 0) * plane_sz + in_plane] = hi;
+    if (P == 2) wp[(stage * P + 1) * plane_sz + in_plane] = lo;
+  }
+  (void)n_tiles;
+}
+ICL_API int icl_pack_w_umma(const float* w, void* wp, int Cout, int Cin, int dgrad, int NT, int P, void* stream) {
+  const int Nn = dgrad ? Cin : Cout, Kk = dgrad ? Cout : Cin;
+  ICL_REQUIRE(Kk % 16 == 0 && Nn % NT == 0 && (P == 1 || P == 2), "pack_w_umma: unsupported shape N=%d K=%d NT=%d P=%d", Nn, Kk, NT, P);
+  pack_w_umma_k<<<grid_for((long long)Nn * Kk * 27, 256), 256, 0, as_stream(stream)>>>((const float*)w, (__nv_bfloat16*)wp, Cout, Cin, dgrad, NT, P);
+  ICL_LAUNCHED("pack_w_umma");
+}
+
+// N tile the kernel will use for a given number of output columns (must divide it).
+ICL_API int icl_umma_ntile(int N) {
+  if (N <= 0 || N % 16 != 0) return 0;
+  if (N <= 128) return N;  // every multiple of 16 up to 256 is a legal UMMA N at M=128
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0) return 96;
+  if (N % 64 == 0) return 64;
+  if (N % 48 == 0) return 48;
+  if (N % 32 == 0) return 32;
+  return 16;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: tensor maps + launch
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+static int make_pk_map(CUtensorMap* map, const void* pk, int P, int B, int C, int D, int H, int W) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { icl_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
+  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)P * B * (C / 8)};
+  const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  const cuuint32_t box[5] = {8, UM_HW, UM_HL, 1, 2};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(pk), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { icl_set_error("cuTensorMapEncodeTiled failed (%d) for PK [%d,%d,%d,%d,%d,%d]", (int)r, P, B, C, D, H, W); return -1; }
+  return 0;
+}
+
+ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1, const void* wp, const float* bias, float* y0, int ld0,
+                                float* y1, int ld1, int split, double* stats, int B, int D, int H, int W, int Cout, int P, int max_ctas,
+                                void* stream) {
+  ICL_REQUIRE(C0 > 0 && C0 % 16 == 0 && C1 % 16 == 0 && Cout % 16 == 0, "conv3d_umma: channels must be multiples of 16 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
+  ICL_REQUIRE(Cout <= UM_MAX_COUT || stats == nullptr, "conv3d_umma: Cout=%d > %d with stats", Cout, UM_MAX_COUT);
+  ICL_REQUIRE(P == 1 || P == 2, "conv3d_umma: P must be 1 or 2");
+  ICL_REQUIRE(split % 16 == 0, "conv3d_umma: split must be a multiple of 16");
+  UmmaConvParams p;
+  p.wp = (const __nv_bfloat16*)wp; p.bias = bias; p.y0 = y0; p.ld0 = ld0; p.y1 = y1 ? y1 : y0; p.ld1 = y1 ? ld1 : ld0;
+  p.split = y1 ? split : Cout; p.stats = stats;
+  if (!y1) { p.split = Cout; }
+  p.B = B; p.D = D; p.H = H; p.W = W; p.C0 = C0; p.C1 = C1; p.Cout = Cout; p.P = P;
+  p.NT = icl_umma_ntile(Cout);
+  ICL_REQUIRE(p.NT >= 16 && Cout % p.NT == 0, "conv3d_umma: no N tile for Cout=%d", Cout);
+  ICL_REQUIRE(y1 == nullptr || split % 16 == 0, "conv3d_umma: bad split");
+  p.n_tiles = Cout / p.NT;
+  p.tiles_h = cdiv(H, UM_TH); p.tiles_w = cdiv(W, UM_TW);
+  p.num_tiles = (long long)B * D * p.tiles_h * p.tiles_w * p.n_tiles;
+  const size_t stage_bytes = (size_t)P * (UM_A_PLANE_BYTES + 9 * p.NT * 32);
+  int stages = (int)((200 * 1024) / stage_bytes);
+  if (stages > UM_MAX_STAGES) stages = UM_MAX_STAGES;
+  ICL_REQUIRE(stages >= 2, "conv3d_umma: stage of %zu bytes does not fit twice in shared memory", stage_bytes);
+  p.stages = stages;
+  int cols = 32;
+  while (cols < 2 * p.NT) cols *= 2;
+  p.tmem_cols = cols;
+  CUtensorMap m0, m1;
+  if (make_pk_map(&m0, pk0, P, B, C0, D, H, W)) return -1;
+  if (C1 > 0) { if (make_pk_map(&m1, pk1, P, B, C1, D, H, W)) return -1; } else m1 = m0;
+  const size_t smem = stage_bytes * stages + 128;
+  static size_t configured = 0;
+  if (smem > configured) {
+    cudaError_t e = cudaFuncSetAttribute(conv3d_umma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024));
+    if (e != cudaSuccess) { icl_set_error("conv3d_umma: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+    configured = 220 * 1024;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  long long grid = p.num_tiles < sms ? p.num_tiles : sms;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
+  conv3d_umma_k<<<(unsigned)grid, 192, smem, as_stream(stream)>>>(m0, m1, p);
+  ICL_LAUNCHED("conv3d_umma_fwd");
+}

@@ -1,0 +1,484 @@
+// Bandwidth-bound activation-side kernels of the 3D U-Net backbone:
+// InstanceNorm3d+ReLU apply / backward, MaxPool3d(2), trilinear x2 upsample, Dropout, and the
+// fp32 -> split-bf16 operand packing that feeds the tcgen05 convolution.
+//
+// Layouts:
+//   F32CL : float  [B][D][H][W][C]                      (torch channels_last_3d of [B,C,D,H,W])
+//   PK    : bf16   [P][B][C/8][D][H][W][8], P=2 planes  (hi, lo) with x ~= hi + lo
+// All kernels are pure streaming: 128/256-bit accesses, voxel-fastest thread mapping so that both
+// the F32CL side (32 B sectors) and the PK side (16 B per voxel, contiguous along W) coalesce.
+#include "common.cuh"
+
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ld8(const float* p) {
+  F8 r; r.a = *reinterpret_cast<const float4*>(p); r.b = *reinterpret_cast<const float4*>(p + 4); return r;
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+  *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+}
+__device__ __forceinline__ void unpack8(const F8& f, float* v) {
+  v[0] = f.a.x; v[1] = f.a.y; v[2] = f.a.z; v[3] = f.a.w; v[4] = f.b.x; v[5] = f.b.y; v[6] = f.b.z; v[7] = f.b.w;
+}
+// writes 8 values as split bf16 into the hi plane (and lo plane when lo != nullptr)
+__device__ __forceinline__ void st_pk8(__nv_bfloat16* hi, __nv_bfloat16* lo, const float* v) {
+  __align__(16) __nv_bfloat16 h[8], l[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) split_bf16(v[i], h[i], l[i]);
+  *reinterpret_cast<uint4*>(hi) = *reinterpret_cast<const uint4*>(h);
+  if (lo) *reinterpret_cast<uint4*>(lo) = *reinterpret_cast<const uint4*>(l);
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm statistics finalize: (sum, sumsq) in double -> (mean, rstd) in float.
+// ------------------------------------------------------------------------------------------
+__global__ void instnorm_finalize_k(const double* __restrict__ stats, float* __restrict__ mr, int n, double inv_count, float eps) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double m = stats[2 * i] * inv_count;
+  double var = stats[2 * i + 1] * inv_count - m * m;
+  if (var < 0) var = 0;
+  mr[2 * i] = (float)m;
+  mr[2 * i + 1] = (float)(1.0 / sqrt(var + (double)eps));
+}
+
+ICL_API int icl_instnorm_finalize(const double* stats, float* mr, int B, int C, long long S, float eps, void* stream) {
+  int n = B * C;
+  instnorm_finalize_k<<<cdiv(n, 128), 128, 0, as_stream(stream)>>>(stats, mr, n, 1.0 / (double)S, eps);
+  ICL_LAUNCHED("instnorm_finalize");
+}
+
+// Plain per-(b,c) sum / sumsq over S for tensors whose producer did not emit statistics.
+__global__ void instnorm_stats_k(const float* __restrict__ y, double* __restrict__ stats, int C, long long S, int chunks) {
+  // grid: (chunks, B); each block reduces a slab of voxels for all C channels (C <= 1024).
+  __shared__ double red[66];
+  const int b = blockIdx.y;
+  const long long per = (S + chunks - 1) / chunks;
+  const long long s0 = (long long)blockIdx.x * per, s1 = min(S, s0 + per);
+  for (int c = 0; c < C; ++c) {
+    double a = 0, q = 0;
+    for (long long s = s0 + threadIdx.x; s < s1; s += blockDim.x) {
+      float v = y[((long long)b * S + s) * C + c];
+      a += v; q += (double)v * v;
+    }
+    a = block_sum_d(a, red);
+    q = block_sum_d(q, red + 33);
+    if (threadIdx.x == 0) {
+      atomicAdd(&stats[((long long)b * C + c) * 2], a);
+      atomicAdd(&stats[((long long)b * C + c) * 2 + 1], q);
+    }
+  }
+}
+ICL_API int icl_instnorm_stats(const float* y, double* stats, int B, int C, long long S, void* stream) {
+  int chunks = (int)min((long long)64, (S + 4095) / 4096);
+  if (chunks < 1) chunks = 1;
+  instnorm_stats_k<<<dim3(chunks, B), 256, 0, as_stream(stream)>>>(y, stats, C, S, chunks);
+  ICL_LAUNCHED("instnorm_stats");
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm + ReLU apply.  a = relu((y - mean) * rstd); optional PK output.
+// grid: (chunks over S, B*C8); block 256.
+// ------------------------------------------------------------------------------------------
+__global__ void instnorm_relu_fwd_k(const float* __restrict__ y, const float* __restrict__ mr, float* __restrict__ a,
+                                    __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, long long S) {
+  const int C8 = C >> 3;
+  const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
+  float mean[8], rstd[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    mean[i] = mr[((long long)b * C + c8 * 8 + i) * 2];
+    rstd[i] = mr[((long long)b * C + c8 * 8 + i) * 2 + 1];
+  }
+  const long long plane = (long long)B * C8 * S * 8;
+  __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    const long long off = ((long long)b * S + s) * C + c8 * 8;
+    float v[8];
+    unpack8(ld8(y + off), v);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = fmaxf((v[i] - mean[i]) * rstd[i], 0.f);
+    if (a) st8(a + off, v);
+    if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, v);
+  }
+}
+__global__ void instnorm_relu_fwd_generic_k(const float* __restrict__ y, const float* __restrict__ mr, float* __restrict__ a,
+                                            int C, long long S, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long b = i / (S * C);
+    const float m = mr[(b * C + c) * 2], r = mr[(b * C + c) * 2 + 1];
+    a[i] = fmaxf((y[i] - m) * r, 0.f);
+  }
+}
+ICL_API int icl_instnorm_relu_fwd(const float* y, const float* mr, float* a, void* pk, int write_lo, int B, int C, long long S,
+                                  void* stream) {
+  if (C % 8 == 0) {
+    int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
+    instnorm_relu_fwd_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(y, mr, a, (__nv_bfloat16*)pk, write_lo, B, C, S);
+  } else {
+    ICL_REQUIRE(pk == nullptr && a != nullptr, "instnorm_relu_fwd: PK output needs C %% 8 == 0 (C=%d)", C);
+    long long total = (long long)B * S * C;
+    instnorm_relu_fwd_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(y, mr, a, C, S, total);
+  }
+  ICL_LAUNCHED("instnorm_relu_fwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// InstanceNorm + ReLU backward:  yh = (y-mean)*rstd, g = dA * [yh > 0],
+//   dY = rstd * (g - mean_S(g) - yh * mean_S(g*yh)).
+// Pass 1 reduces (sum g, sum g*yh) per (b,c); pass 2 applies and optionally emits dY as PK and
+// accumulates sum_S dY (the conv-bias gradient; mathematically ~0 for InstanceNorm).
+// ------------------------------------------------------------------------------------------
+__global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
+                                           double* __restrict__ red, int C, long long S, int chunks) {
+  // grid (chunks, B); thread t owns channel group: channels handled as c = t % C lanes when C <= blockDim
+  // Generic mapping: each thread walks elements i = s*C + c with stride blockDim (C divides blockDim or not).
+  extern __shared__ double sm[];  // [2][C]
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.0;
+  __syncthreads();
+  const long long per = (S + chunks - 1) / chunks;
+  const long long s0 = (long long)blockIdx.x * per, s1 = min(S, s0 + per);
+  const long long n = (s1 - s0) * C;
+  const float* dAb = dA + ((long long)b * S + s0) * C;
+  const float* yb = y + ((long long)b * S + s0) * C;
+  // When blockDim % C == 0 every thread keeps a fixed channel -> accumulate in registers.
+  if (blockDim.x % C == 0) {
+    const int c = threadIdx.x % C;
+    const float m = mr[((long long)b * C + c) * 2], r = mr[((long long)b * C + c) * 2 + 1];
+    float sg = 0.f, sgy = 0.f;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const float yh = (yb[i] - m) * r;
+      const float g = yh > 0.f ? dAb[i] : 0.f;
+      sg += g; sgy += g * yh;
+    }
+    atomicAdd(&sm[c], (double)sg);
+    atomicAdd(&sm[C + c], (double)sgy);
+  } else {
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const int c = (int)(i % C);
+      const float m = mr[((long long)b * C + c) * 2], r = mr[((long long)b * C + c) * 2 + 1];
+      const float yh = (yb[i] - m) * r;
+      const float g = yh > 0.f ? dAb[i] : 0.f;
+      atomicAdd(&sm[c], (double)g);
+      atomicAdd(&sm[C + c], (double)(g * yh));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    atomicAdd(&red[((long long)b * C + i) * 2], sm[i]);
+    atomicAdd(&red[((long long)b * C + i) * 2 + 1], sm[C + i]);
+  }
+}
+
+__global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
+                                          const double* __restrict__ red, float* __restrict__ dY, __nv_bfloat16* __restrict__ pk,
+                                          int write_lo, int B, int C, long long S) {
+  const int C8 = C >> 3;
+  const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
+  float mean[8], rstd[8], mg[8], mgy[8];
+  const float invS = 1.f / (float)S;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long k = (long long)b * C + c8 * 8 + i;
+    mean[i] = mr[k * 2]; rstd[i] = mr[k * 2 + 1];
+    mg[i] = (float)(red[k * 2] / (double)S); mgy[i] = (float)(red[k * 2 + 1] / (double)S);
+  }
+  (void)invS;
+  const long long plane = (long long)B * C8 * S * 8;
+  __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    const long long off = ((long long)b * S + s) * C + c8 * 8;
+    float yv[8], gv[8], o[8];
+    unpack8(ld8(y + off), yv);
+    unpack8(ld8(dA + off), gv);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float yh = (yv[i] - mean[i]) * rstd[i];
+      const float g = yh > 0.f ? gv[i] : 0.f;
+      o[i] = rstd[i] * (g - mg[i] - yh * mgy[i]);
+    }
+    if (dY) st8(dY + off, o);
+    if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, o);
+  }
+}
+__global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
+                                                  const double* __restrict__ red, float* __restrict__ dY, int C, long long S, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long k = (i / (S * C)) * C + c;
+    const float m = mr[k * 2], r = mr[k * 2 + 1];
+    const float mg = (float)(red[k * 2] / (double)S), mgy = (float)(red[k * 2 + 1] / (double)S);
+    const float yh = (y[i] - m) * r;
+    const float g = yh > 0.f ? dA[i] : 0.f;
+    dY[i] = r * (g - mg - yh * mgy);
+  }
+}
+ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red /* [B,C,2] zeroed */, float* dY,
+                                  void* pk, int write_lo, int B, int C, long long S, void* stream) {
+  ICL_REQUIRE(C <= 1024, "instnorm_relu_bwd: C=%d > 1024", C);
+  int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 65535) / 65536);
+  if (chunks < 1) chunks = 1;
+  instnorm_relu_bwd_reduce_k<<<dim3(chunks, B), 256, 2 * C * sizeof(double), as_stream(stream)>>>(dA, y, mr, red, C, S, chunks);
+  icl_count_launch(1);
+  if (C % 8 == 0) {
+    int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
+    instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S);
+  } else {
+    ICL_REQUIRE(pk == nullptr && dY != nullptr, "instnorm_relu_bwd: PK output needs C %% 8 == 0 (C=%d)", C);
+    long long total = (long long)B * S * C;
+    instnorm_relu_bwd_apply_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, C, S, total);
+  }
+  ICL_LAUNCHED("instnorm_relu_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 F32CL -> PK split-bf16 operand (C % 8 == 0).
+// ------------------------------------------------------------------------------------------
+__global__ void pack_pk_k(const float* __restrict__ x, __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, long long S) {
+  const int C8 = C >> 3;
+  const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
+  const long long plane = (long long)B * C8 * S * 8;
+  __nv_bfloat16* hi = pk + ((long long)b * C8 + c8) * S * 8;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    float v[8];
+    unpack8(ld8(x + ((long long)b * S + s) * C + c8 * 8), v);
+    st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, v);
+  }
+}
+ICL_API int icl_pack_pk(const float* x, void* pk, int write_lo, int B, int C, long long S, void* stream) {
+  ICL_REQUIRE(C % 8 == 0, "pack_pk: C=%d not a multiple of 8", C);
+  int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
+  pack_pk_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(x, (__nv_bfloat16*)pk, write_lo, B, C, S);
+  ICL_LAUNCHED("pack_pk");
+}
+
+// ------------------------------------------------------------------------------------------
+// MaxPool3d(2) forward/backward.  First maximum in (d,h,w) scan order wins ties:
+// strict '>' while scanning; NaN propagates like torch (val != val takes over).
+// idx stores the winning position 0..7 per output element.
+// ------------------------------------------------------------------------------------------
+__global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ out, unsigned char* __restrict__ idx,
+                              __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, int D, int H, int W) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long So = (long long)Do * Ho * Wo;
+  const long long total = (long long)B * So * C;
+  const int C8 = (C % 8 == 0) ? C / 8 : 0;
+  const long long plane = (long long)B * C8 * So * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int wo = (int)(v % Wo); v /= Wo;
+    const int ho = (int)(v % Ho); v /= Ho;
+    const int dd = (int)(v % Do);
+    const int b = (int)(v / Do);
+    float best = 0.f; int bi = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+      const int d = 2 * dd + (p >> 2), h = 2 * ho + ((p >> 1) & 1), w = 2 * wo + (p & 1);
+      const float val = x[((((long long)b * D + d) * H + h) * W + w) * C + c];
+      if (p == 0 || val > best || val != val) { best = val; bi = p; }
+    }
+    out[i] = best;
+    idx[i] = (unsigned char)bi;
+    if (pk) {
+      const long long s = ((long long)dd * Ho + ho) * Wo + wo;
+      __nv_bfloat16 hi, lo; split_bf16(best, hi, lo);
+      const long long o = (((long long)b * C8 + (c >> 3)) * So + s) * 8 + (c & 7);
+      pk[o] = hi;
+      if (write_lo) pk[plane + o] = lo;
+    }
+  }
+}
+ICL_API int icl_maxpool3d_fwd(const float* x, float* out, unsigned char* idx, void* pk, int write_lo, int B, int C, int D, int H, int W,
+                              void* stream) {
+  ICL_REQUIRE(D % 2 == 0 && H % 2 == 0 && W % 2 == 0, "maxpool3d: odd spatial size %dx%dx%d", D, H, W);
+  ICL_REQUIRE(pk == nullptr || C % 8 == 0, "maxpool3d: PK output needs C %% 8 == 0");
+  long long total = (long long)B * C * (D / 2) * (H / 2) * (W / 2);
+  maxpool_fwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, out, idx, (__nv_bfloat16*)pk, write_lo, B, C, D, H, W);
+  ICL_LAUNCHED("maxpool3d_fwd");
+}
+
+// dx[in voxel] (+)= (idx[out voxel] == my position) ? dout : 0     (gather form, no atomics)
+__global__ void maxpool_bwd_k(const float* __restrict__ dout, const unsigned char* __restrict__ idx, float* __restrict__ dx, int accumulate,
+                              int B, int C, int D, int H, int W) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * D * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H); v /= H;
+    const int d = (int)(v % D);
+    const int b = (int)(v / D);
+    const long long o = ((((long long)b * Do + d / 2) * Ho + h / 2) * Wo + w / 2) * C + c;
+    const int p = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+    const float g = (idx[o] == p) ? dout[o] : 0.f;
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+ICL_API int icl_maxpool3d_bwd(const float* dout, const unsigned char* idx, float* dx, int accumulate, int B, int C, int D, int H, int W,
+                              void* stream) {
+  long long total = (long long)B * C * D * H * W;
+  maxpool_bwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dout, idx, dx, accumulate, B, C, D, H, W);
+  ICL_LAUNCHED("maxpool3d_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Trilinear x2 upsample, align_corners=False: src = (dst+0.5)/2 - 0.5 clamped at 0.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void up2_src(int j, int n, int& i0, int& i1, float& l1) {
+  float s = (j + 0.5f) * 0.5f - 0.5f;
+  if (s < 0.f) s = 0.f;
+  i0 = (int)s;
+  i1 = min(i0 + 1, n - 1);
+  l1 = s - (float)i0;
+}
+__global__ void upsample2x_fwd_k(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ pk, int write_lo,
+                                 int B, int C, int d, int h, int w) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const long long S = (long long)D * H * W;
+  const long long total = (long long)B * S * C;
+  const int C8 = (C % 8 == 0) ? C / 8 : 0;
+  const long long plane = (long long)B * C8 * S * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int X = (int)(v % W); v /= W;
+    const int Y = (int)(v % H); v /= H;
+    const int Z = (int)(v % D);
+    const int b = (int)(v / D);
+    int z0, z1, y0, y1, x0, x1; float lz, ly, lx;
+    up2_src(Z, d, z0, z1, lz); up2_src(Y, h, y0, y1, ly); up2_src(X, w, x0, x1, lx);
+    const float* xb = x + (long long)b * d * h * w * C + c;
+#define AT(zz, yy, xx) xb[(((long long)(zz) * h + (yy)) * w + (xx)) * C]
+    // same association order as ATen's upsample_trilinear3d: w-lerp inside h-lerp inside d-lerp
+    const float v00 = (1.f - lx) * AT(z0, y0, x0) + lx * AT(z0, y0, x1);
+    const float v01 = (1.f - lx) * AT(z0, y1, x0) + lx * AT(z0, y1, x1);
+    const float v10 = (1.f - lx) * AT(z1, y0, x0) + lx * AT(z1, y0, x1);
+    const float v11 = (1.f - lx) * AT(z1, y1, x0) + lx * AT(z1, y1, x1);
+#undef AT
+    const float r = (1.f - lz) * ((1.f - ly) * v00 + ly * v01) + lz * ((1.f - ly) * v10 + ly * v11);
+    if (out) out[i] = r;
+    if (pk) {
+      const long long s = ((long long)Z * H + Y) * W + X;
+      __nv_bfloat16 hi, lo; split_bf16(r, hi, lo);
+      const long long o = (((long long)b * C8 + (c >> 3)) * S + s) * 8 + (c & 7);
+      pk[o] = hi;
+      if (write_lo) pk[plane + o] = lo;
+    }
+  }
+}
+ICL_API int icl_upsample2x_fwd(const float* x, float* out, void* pk, int write_lo, int B, int C, int d, int h, int w, void* stream) {
+  ICL_REQUIRE(pk == nullptr || C % 8 == 0, "upsample2x: PK output needs C %% 8 == 0");
+  long long total = (long long)B * C * 8 * d * h * w;
+  upsample2x_fwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, B, C, d, h, w);
+  ICL_LAUNCHED("upsample2x_fwd");
+}
+
+// adjoint in gather form: coarse voxel i collects from fine j in [2i-1, 2i+2]
+__device__ __forceinline__ float up2_wt(int j, int n, int i) {
+  if (j < 0 || j >= 2 * n) return 0.f;
+  int i0, i1; float l1;
+  up2_src(j, n, i0, i1, l1);
+  float wgt = 0.f;
+  if (i0 == i) wgt += 1.f - l1;
+  if (i1 == i) wgt += l1;
+  return wgt;
+}
+__global__ void upsample2x_bwd_k(const float* __restrict__ dout, int Cd, int c_off, float* __restrict__ dx, int accumulate,
+                                 int B, int C, int d, int h, int w) {
+  // dout is F32CL with Cd channels; this op's channels start at c_off (lets the caller pass the
+  // [skip|up] gradient of a concatenated conv input without slicing).
+  const int D = 2 * d, H = 2 * h, W = 2 * w;
+  const long long total = (long long)B * d * h * w * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int x = (int)(v % w); v /= w;
+    const int y = (int)(v % h); v /= h;
+    const int z = (int)(v % d);
+    const int b = (int)(v / d);
+    float acc = 0.f;
+    for (int dz = -1; dz <= 2; ++dz) {
+      const int Z = 2 * z + dz; const float wz = up2_wt(Z, d, z);
+      if (wz == 0.f) continue;
+      for (int dy = -1; dy <= 2; ++dy) {
+        const int Y = 2 * y + dy; const float wy = up2_wt(Y, h, y);
+        if (wy == 0.f) continue;
+        for (int dxx = -1; dxx <= 2; ++dxx) {
+          const int X = 2 * x + dxx; const float wx = up2_wt(X, w, x);
+          if (wx == 0.f) continue;
+          acc += wz * wy * wx * dout[((((long long)b * D + Z) * H + Y) * W + X) * Cd + c_off + c];
+        }
+      }
+    }
+    dx[i] = accumulate ? dx[i] + acc : acc;
+  }
+}
+ICL_API int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int B, int C, int d, int h, int w,
+                               void* stream) {
+  long long total = (long long)B * C * d * h * w;
+  upsample2x_bwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate, B, C, d, h, w);
+  ICL_LAUNCHED("upsample2x_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Dropout (inverted, p): out = x * keep / (1-p).  keep comes either from an explicit byte mask
+// (parity tests replay torch-drawn masks) or from Philox4x32 keyed by (seed, element index / 4),
+// regenerated identically in backward so no mask is stored.
+// ------------------------------------------------------------------------------------------
+__global__ void dropout_k(const float* __restrict__ x, float* __restrict__ out, const unsigned char* __restrict__ mask,
+                          unsigned long long seed, float p, long long total) {
+  const float scale = 1.f / (1.f - p);
+  const long long n4 = (total + 3) / 4;
+  for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
+    uint4 r = make_uint4(0, 0, 0, 0);
+    if (!mask) r = philox4x32(make_uint4((uint32_t)q, (uint32_t)(q >> 32), 0x1c1u, 0xb200u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long i = q * 4 + j;
+      if (i >= total) break;
+      bool keep;
+      if (mask) keep = mask[i] != 0;
+      else keep = (rr[j] >> 8) * (1.0f / 16777216.0f) >= p;
+      out[i] = keep ? x[i] * scale : 0.f;
+    }
+  }
+}
+ICL_API int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, float p, long long total,
+                        void* stream) {
+  ICL_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
+  dropout_k<<<grid_for((total + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, out, mask, seed, p, total);
+  ICL_LAUNCHED("dropout");
+}
+
+// ------------------------------------------------------------------------------------------
+// small utilities:  y = alpha*x + beta*y ;  rows scaled by a per-row factor (DropPath)
+// ------------------------------------------------------------------------------------------
+__global__ void axpby_k(const float* __restrict__ x, float* __restrict__ y, float alpha, float beta, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i] + (beta == 0.f ? 0.f : beta * y[i]);
+}
+ICL_API int icl_axpby(const float* x, float* y, float alpha, float beta, long long n, void* stream) {
+  axpby_k<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(x, y, alpha, beta, n);
+  ICL_LAUNCHED("axpby");
+}
+// out[r, :] = a[r, :] * sa[r] + b[r, :] * sb[r]   (sa/sb may be null => 1)
+__global__ void row_combine_k(const float* __restrict__ a, const float* __restrict__ sa, const float* __restrict__ b,
+                              const float* __restrict__ sb, float* __restrict__ out, long long rows, long long cols) {
+  const long long n = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols;
+    float v = a[i] * (sa ? sa[r] : 1.f);
+    if (b) v += b[i] * (sb ? sb[r] : 1.f);
+    out[i] = v;
+  }
+}
+ICL_API int icl_row_combine(const float* a, const float* sa, const float* b, const float* sb, float* out, long long rows, long long cols,
+                            void* stream) {
+  row_combine_k<<<grid_for(rows * cols, 256), 256, 0, as_stream(stream)>>>(a, sa, b, sb, out, rows, cols);
+  ICL_LAUNCHED("row_combine");
+}

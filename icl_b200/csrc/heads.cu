@@ -1,0 +1,427 @@
+// Kernels of the Inherent-Consistent-Learning heads:
+// LayerNorm over the last axis (C or the spatial axis N), the voxel -> class-proxy cross
+// attention (Query_Attention, networks/unet_3D_icl.py:283-297) and the depthwise-separable
+// conv + batch-stat BatchNorm3d stack (SeparableConv3d, :317-345) on planar [B*K, H, d,h,w] maps.
+// All are bandwidth/latency bound: coalesced streaming + warp-shuffle reductions, fp32 math.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// LayerNorm over the last axis, one block per row.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) layernorm_fwd_k(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ b,
+                                                       float* __restrict__ y, float* __restrict__ mean_rstd, int C, float eps) {
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  const float* xr = x + row * C;
+  float s = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) s += xr[i];
+  const float mean = block_sum(s, red) / C;
+  float q = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) { const float d = xr[i] - mean; q += d * d; }
+  const float var = block_sum(q, red) / C;
+  const float rstd = rsqrtf(var + eps);
+  for (int i = threadIdx.x; i < C; i += blockDim.x) y[row * C + i] = (xr[i] - mean) * rstd * w[i] + b[i];
+  if (threadIdx.x == 0) { mean_rstd[row * 2] = mean; mean_rstd[row * 2 + 1] = rstd; }
+}
+ICL_API int icl_layernorm_fwd(const float* x, const float* w, const float* b, float* y, float* mean_rstd, long long rows, int C, float eps,
+                              void* stream) {
+  ICL_REQUIRE(rows > 0 && rows < 2147483647LL, "layernorm_fwd: bad rows");
+  layernorm_fwd_k<<<(unsigned)rows, C >= 1024 ? 256 : (C >= 128 ? 128 : 64), 0, as_stream(stream)>>>(x, w, b, y, mean_rstd, C, eps);
+  ICL_LAUNCHED("layernorm_fwd");
+}
+
+// dx = rstd * (dy*w - mean(dy*w) - xh * mean(dy*w*xh))
+__global__ void __launch_bounds__(256) layernorm_bwd_dx_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ w,
+                                                          const float* __restrict__ mean_rstd, float* __restrict__ dx, int C) {
+  __shared__ float red[33];
+  const long long row = blockIdx.x;
+  const float mean = mean_rstd[row * 2], rstd = mean_rstd[row * 2 + 1];
+  const float* xr = x + row * C; const float* gr = dy + row * C;
+  float a = 0.f, c = 0.f;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float g = gr[i] * w[i], xh = (xr[i] - mean) * rstd;
+    a += g; c += g * xh;
+  }
+  a = block_sum(a, red) / C;
+  c = block_sum(c, red) / C;
+  for (int i = threadIdx.x; i < C; i += blockDim.x) {
+    const float g = gr[i] * w[i], xh = (xr[i] - mean) * rstd;
+    dx[row * C + i] = rstd * (g - a - xh * c);
+  }
+}
+// dw[c] += sum_rows dy*xh ; db[c] += sum_rows dy.  grid (col tiles of 32, row chunks); atomics at the end.
+__global__ void __launch_bounds__(256) layernorm_bwd_wb_k(const float* __restrict__ dy, const float* __restrict__ x,
+                                                          const float* __restrict__ mean_rstd, float* __restrict__ dw, float* __restrict__ db,
+                                                          long long rows, int C, long long rows_per) {
+  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int rl = threadIdx.x >> 5;
+  const long long r0 = (long long)blockIdx.y * rows_per, r1 = min(rows, r0 + rows_per);
+  float a = 0.f, bsum = 0.f;
+  if (c < C)
+    for (long long r = r0 + rl; r < r1; r += 8) {
+      const float g = dy[r * C + c];
+      a += g * (x[r * C + c] - mean_rstd[r * 2]) * mean_rstd[r * 2 + 1];
+      bsum += g;
+    }
+  __shared__ float red[2][8][33];
+  red[0][rl][threadIdx.x & 31] = a; red[1][rl][threadIdx.x & 31] = bsum;
+  __syncthreads();
+  if (rl == 0 && c < C) {
+    float ta = 0.f, tb = 0.f;
+    for (int k = 0; k < 8; ++k) { ta += red[0][k][threadIdx.x & 31]; tb += red[1][k][threadIdx.x & 31]; }
+    atomicAdd(&dw[c], ta); atomicAdd(&db[c], tb);
+  }
+}
+ICL_API int icl_layernorm_bwd(const float* dy, const float* x, const float* w, const float* mean_rstd, float* dx, float* dw, float* db,
+                              long long rows, int C, void* stream) {
+  if (dx) {
+    layernorm_bwd_dx_k<<<(unsigned)rows, C >= 1024 ? 256 : (C >= 128 ? 128 : 64), 0, as_stream(stream)>>>(dy, x, w, mean_rstd, dx, C);
+    icl_count_launch(1);
+  }
+  if (dw) {  // dw / db must be zero-initialised (or hold the value to accumulate into)
+    const int gx = cdiv(C, 32);
+    int gy = (int)max((long long)1, min((rows + 63) / 64, (long long)max(1, 148 * 4 / gx)));
+    const long long rows_per = (rows + gy - 1) / gy;
+    layernorm_bwd_wb_k<<<dim3(gx, gy), 256, 0, as_stream(stream)>>>(dy, x, mean_rstd, dw, db, rows, C, rows_per);
+    icl_count_launch(1);
+  }
+  return icl_check_launch("layernorm_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Proxy cross-attention.  ql: fc_q output, flat [B, K*C] read as [B,H,K,hd];
+// kv: fc_kv output [B,N,2C].  map[b,k,h,n] = scale * <q[b,h,k,:], k[b,n,h,:]> (PRE-softmax, the
+// tensor the reference returns); xv[b,h,k,:] = sum_n softmax_n(map[b,k,h,:])[n] * v[b,n,h,:].
+// ------------------------------------------------------------------------------------------
+#define PA_MAXHD 64
+__global__ void __launch_bounds__(256) proxy_logits_k(const float* __restrict__ ql, const float* __restrict__ kv, float* __restrict__ map,
+                                                      int B, int N, int C, int H, int K, float scale) {
+  extern __shared__ float qs[];  // [K][hd] for this (b, h)
+  const int hd = C / H;
+  const int b = blockIdx.z, h = blockIdx.y;
+  for (int i = threadIdx.x; i < K * hd; i += blockDim.x) qs[i] = ql[(long long)b * K * C + (long long)h * K * hd + i];
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    float kr[PA_MAXHD];
+    const float* kp = kv + ((long long)b * N + n) * 2 * C + h * hd;
+#pragma unroll 4
+    for (int d = 0; d < hd; ++d) kr[d] = kp[d];
+    for (int k = 0; k < K; ++k) {
+      float s = 0.f;
+      for (int d = 0; d < hd; ++d) s = fmaf(qs[k * hd + d], kr[d], s);
+      map[(((long long)b * K + k) * H + h) * N + n] = s * scale;
+    }
+  }
+}
+// one block per (b,h,k): softmax stats over N and xv
+__global__ void __launch_bounds__(256) proxy_av_k(const float* __restrict__ map, const float* __restrict__ kv, float* __restrict__ xv,
+                                                  float* __restrict__ mstat, int B, int N, int C, int H, int K) {
+  __shared__ float red[33];
+  __shared__ float accs[8][PA_MAXHD];
+  const int hd = C / H;
+  int id = blockIdx.x;
+  const int k = id % K; id /= K;
+  const int h = id % H; const int b = id / H;
+  const float* row = map + (((long long)b * K + k) * H + h) * N;
+  float mx = -INFINITY;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) mx = fmaxf(mx, row[n]);
+  mx = warp_max(mx);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = mx;
+  __syncthreads();
+  mx = -INFINITY;
+  for (int i = 0; i < (blockDim.x >> 5); ++i) mx = fmaxf(mx, red[i]);
+  __syncthreads();
+  float se = 0.f;
+  float acc[PA_MAXHD];
+  for (int d = 0; d < hd; ++d) acc[d] = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    const float e = __expf(row[n] - mx);
+    se += e;
+    const float* vp = kv + ((long long)b * N + n) * 2 * C + C + h * hd;
+    for (int d = 0; d < hd; ++d) acc[d] = fmaf(e, vp[d], acc[d]);
+  }
+  se = block_sum(se, red);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = 0; d < hd; ++d) {
+    const float s = warp_sum(acc[d]);
+    if (lane == 0) accs[wid][d] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < hd) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += accs[i][threadIdx.x];
+    xv[(long long)b * K * C + ((long long)h * K + k) * hd + threadIdx.x] = s / se;
+  }
+  if (threadIdx.x == 0) { mstat[blockIdx.x * 2] = mx; mstat[blockIdx.x * 2 + 1] = se; }
+}
+ICL_API int icl_proxy_attn_fwd(const float* ql, const float* kv, float* map, float* xv, float* mstat, int B, int N, int C, int H, int K,
+                               float scale, int want_xv, void* stream) {
+  const int hd = C / H;
+  ICL_REQUIRE(C % H == 0 && hd <= PA_MAXHD, "proxy_attn: head_dim %d unsupported (max %d)", hd, PA_MAXHD);
+  proxy_logits_k<<<dim3(cdiv(N, 256), H, B), 256, K * hd * sizeof(float), as_stream(stream)>>>(ql, kv, map, B, N, C, H, K, scale);
+  icl_count_launch(1);
+  if (want_xv) {
+    proxy_av_k<<<B * H * K, 256, 0, as_stream(stream)>>>(map, kv, xv, mstat, B, N, C, H, K);
+    icl_count_launch(1);
+  }
+  return icl_check_launch("proxy_attn_fwd");
+}
+
+// backward, stage 1 (block per (b,h,k)): total gradient of the logits
+//   dl[n] = dmap[n] + p[n] * (dP[n] - sum_n' p[n'] dP[n']),  dP[n] = <dxv, v[n]>   (second term only if dxv)
+// written to dl (may alias a scratch buffer), and dq[b,h,k,:] = scale * sum_n dl[n] * k[n,:].
+__global__ void __launch_bounds__(256) proxy_bwd1_k(const float* __restrict__ dmap, const float* __restrict__ dxv, const float* __restrict__ map,
+                                                    const float* __restrict__ kv, const float* __restrict__ mstat, float* __restrict__ dl,
+                                                    float* __restrict__ dql, int B, int N, int C, int H, int K, float scale) {
+  __shared__ float red[33];
+  __shared__ float accs[8][PA_MAXHD];
+  __shared__ float gx[PA_MAXHD];
+  const int hd = C / H;
+  int id = blockIdx.x;
+  const int k = id % K; id /= K;
+  const int h = id % H; const int b = id / H;
+  const long long ro = (((long long)b * K + k) * H + h) * N;
+  float Dsum = 0.f;
+  const float mx = mstat ? mstat[blockIdx.x * 2] : 0.f, inv = mstat ? 1.f / mstat[blockIdx.x * 2 + 1] : 0.f;
+  if (dxv) {
+    if (threadIdx.x < hd) gx[threadIdx.x] = dxv[(long long)b * K * C + ((long long)h * K + k) * hd + threadIdx.x];
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += blockDim.x) {
+      const float p = __expf(map[ro + n] - mx) * inv;
+      const float* vp = kv + ((long long)b * N + n) * 2 * C + C + h * hd;
+      float dP = 0.f;
+      for (int d = 0; d < hd; ++d) dP = fmaf(gx[d], vp[d], dP);
+      Dsum += p * dP;
+    }
+    Dsum = block_sum(Dsum, red);
+  }
+  float acc[PA_MAXHD];
+  for (int d = 0; d < hd; ++d) acc[d] = 0.f;
+  for (int n = threadIdx.x; n < N; n += blockDim.x) {
+    float g = dmap ? dmap[ro + n] : 0.f;
+    if (dxv) {
+      const float p = __expf(map[ro + n] - mx) * inv;
+      const float* vp = kv + ((long long)b * N + n) * 2 * C + C + h * hd;
+      float dP = 0.f;
+      for (int d = 0; d < hd; ++d) dP = fmaf(gx[d], vp[d], dP);
+      g += p * (dP - Dsum);
+    }
+    dl[ro + n] = g;
+    const float* kp = kv + ((long long)b * N + n) * 2 * C + h * hd;
+    for (int d = 0; d < hd; ++d) acc[d] = fmaf(g, kp[d], acc[d]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  for (int d = 0; d < hd; ++d) {
+    const float s = warp_sum(acc[d]);
+    if (lane == 0) accs[wid][d] = s;
+  }
+  __syncthreads();
+  if (threadIdx.x < hd) {
+    float s = 0.f;
+    for (int i = 0; i < (blockDim.x >> 5); ++i) s += accs[i][threadIdx.x];
+    dql[(long long)b * K * C + ((long long)h * K + k) * hd + threadIdx.x] = s * scale;
+  }
+}
+// stage 2 (thread per (b,n,h)): dk = scale * sum_k dl[k,n] q[k,:],  dv = sum_k p[k,n] dxv[k,:]
+__global__ void __launch_bounds__(256) proxy_bwd2_k(const float* __restrict__ dl, const float* __restrict__ dxv, const float* __restrict__ map,
+                                                    const float* __restrict__ ql, const float* __restrict__ mstat, float* __restrict__ dkv,
+                                                    int B, int N, int C, int H, int K, float scale) {
+  extern __shared__ float sm[];  // qs[K*hd], gs[K*hd], ms[2K]
+  const int hd = C / H;
+  float* qs = sm; float* gs = sm + K * hd; float* ms = gs + K * hd;
+  const int b = blockIdx.z, h = blockIdx.y;
+  for (int i = threadIdx.x; i < K * hd; i += blockDim.x) {
+    qs[i] = ql[(long long)b * K * C + (long long)h * K * hd + i];
+    gs[i] = dxv ? dxv[(long long)b * K * C + (long long)h * K * hd + i] : 0.f;
+  }
+  for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const int id = (b * H + h) * K + i;
+    ms[2 * i] = mstat ? mstat[id * 2] : 0.f; ms[2 * i + 1] = mstat ? 1.f / mstat[id * 2 + 1] : 0.f;
+  }
+  __syncthreads();
+  for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+    float dk[PA_MAXHD], dv[PA_MAXHD];
+    for (int d = 0; d < hd; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int k = 0; k < K; ++k) {
+      const long long o = (((long long)b * K + k) * H + h) * N + n;
+      const float g = dl[o] * scale;
+      for (int d = 0; d < hd; ++d) dk[d] = fmaf(g, qs[k * hd + d], dk[d]);
+      if (dxv) {
+        const float p = __expf(map[o] - ms[2 * k]) * ms[2 * k + 1];
+        for (int d = 0; d < hd; ++d) dv[d] = fmaf(p, gs[k * hd + d], dv[d]);
+      }
+    }
+    float* o = dkv + ((long long)b * N + n) * 2 * C + h * hd;
+    for (int d = 0; d < hd; ++d) { o[d] = dk[d]; o[C + d] = dv[d]; }
+  }
+}
+ICL_API int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* map, const float* ql, const float* kv, const float* mstat,
+                               float* dl_scratch, float* dql, float* dkv, int B, int N, int C, int H, int K, float scale, void* stream) {
+  const int hd = C / H;
+  ICL_REQUIRE(C % H == 0 && hd <= PA_MAXHD, "proxy_attn_bwd: head_dim %d unsupported", hd);
+  ICL_REQUIRE(dxv == nullptr || mstat != nullptr, "proxy_attn_bwd: softmax stats required when dxv is given");
+  proxy_bwd1_k<<<B * H * K, 256, 0, as_stream(stream)>>>(dmap, dxv, map, kv, mstat, dl_scratch, dql, B, N, C, H, K, scale);
+  icl_count_launch(1);
+  proxy_bwd2_k<<<dim3(cdiv(N, 256), H, B), 256, (2 * K * hd + 2 * K) * sizeof(float), as_stream(stream)>>>(
+      dl_scratch, dxv, map, ql, mstat, dkv, B, N, C, H, K, scale);
+  icl_count_launch(1);
+  return icl_check_launch("proxy_attn_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// Planar [NB, CH, d, h, w] depthwise 3x3x3 conv (groups = CH, no bias, zero pad 1).
+// flip = 1 gives the data gradient (correlation with the flipped kernel).
+// ------------------------------------------------------------------------------------------
+__global__ void dwconv3d_k(const float* __restrict__ x, const float* __restrict__ w, float* __restrict__ y, int NB, int CH, int d, int h,
+                           int wd, int flip) {
+  const long long S = (long long)d * h * wd, total = (long long)NB * CH * S;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    long long v = i;
+    const int xx = (int)(v % wd); v /= wd;
+    const int yy = (int)(v % h); v /= h;
+    const int zz = (int)(v % d); v /= d;
+    const int c = (int)(v % CH);
+    const float* xp = x + (i - (((long long)zz * h + yy) * wd + xx));
+    const float* wp = w + c * 27;
+    float s = 0.f;
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int z = zz + t / 9 - 1, yq = yy + (t / 3) % 3 - 1, xq = xx + t % 3 - 1;
+      if (z >= 0 && z < d && yq >= 0 && yq < h && xq >= 0 && xq < wd)
+        s = fmaf(xp[((long long)z * h + yq) * wd + xq], wp[flip ? 26 - t : t], s);
+    }
+    y[i] = s;
+  }
+}
+ICL_API int icl_dwconv3d(const float* x, const float* w, float* y, int NB, int CH, int d, int h, int wd, int flip, void* stream) {
+  dwconv3d_k<<<grid_for((long long)NB * CH * d * h * wd, 256), 256, 0, as_stream(stream)>>>(x, w, y, NB, CH, d, h, wd, flip);
+  ICL_LAUNCHED("dwconv3d");
+}
+// dw[c][t] = sum_{nb, v} x[nb,c,v+t-1] * dy[nb,c,v]; one block per (c, t)
+__global__ void __launch_bounds__(256) dwconv3d_wgrad_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                        int NB, int CH, int d, int h, int wd) {
+  __shared__ float red[33];
+  const int c = blockIdx.x / 27, t = blockIdx.x % 27;
+  const int oz = t / 9 - 1, oy = (t / 3) % 3 - 1, ox = t % 3 - 1;
+  const long long S = (long long)d * h * wd;
+  float s = 0.f;
+  for (long long i = threadIdx.x; i < (long long)NB * S; i += blockDim.x) {
+    const long long nb = i / S; long long v = i % S;
+    const int xx = (int)(v % wd); v /= wd;
+    const int yy = (int)(v % h); const int zz = (int)(v / h);
+    const int z = zz + oz, yq = yy + oy, xq = xx + ox;
+    if (z >= 0 && z < d && yq >= 0 && yq < h && xq >= 0 && xq < wd) {
+      const long long base = (nb * CH + c) * S;
+      s = fmaf(x[base + ((long long)z * h + yq) * wd + xq], dy[base + ((long long)zz * h + yy) * wd + xx], s);
+    }
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) dw[blockIdx.x] = s;
+}
+ICL_API int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int NB, int CH, int d, int h, int wd, void* stream) {
+  dwconv3d_wgrad_k<<<CH * 27, 256, 0, as_stream(stream)>>>(x, dy, dw, NB, CH, d, h, wd);
+  ICL_LAUNCHED("dwconv3d_wgrad");
+}
+
+// ------------------------------------------------------------------------------------------
+// BatchNorm3d in training mode + ReLU on planar [NB, CH, S]: batch statistics per channel over
+// NB*S (biased var for normalisation, unbiased for the running update, momentum 0.1).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(512) bn_stats_k(const float* __restrict__ x, float* __restrict__ mean_rstd, float* __restrict__ run_mean,
+                                                  float* __restrict__ run_var, int NB, int CH, long long S, float eps, float momentum) {
+  __shared__ double red[66];
+  const int c = blockIdx.x;
+  const long long n = (long long)NB * S;
+  double a = 0.0, q = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = x[((i / S) * CH + c) * S + (i % S)];
+    a += v; q += (double)v * v;
+  }
+  a = block_sum_d(a, red); q = block_sum_d(q, red + 33);
+  if (threadIdx.x == 0) {
+    const double m = a / n;
+    double var = q / n - m * m;
+    if (var < 0) var = 0;
+    mean_rstd[2 * c] = (float)m;
+    mean_rstd[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
+    if (run_mean) {
+      const double unb = n > 1 ? var * (double)n / (double)(n - 1) : var;
+      run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
+      run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
+    }
+  }
+}
+__global__ void bn_relu_apply_k(const float* __restrict__ x, const float* __restrict__ mean_rstd, const float* __restrict__ g,
+                                const float* __restrict__ b, float* __restrict__ y, int CH, long long S, long long total) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / S) % CH);
+    y[i] = fmaxf((x[i] - mean_rstd[2 * c]) * mean_rstd[2 * c + 1] * g[c] + b[c], 0.f);
+  }
+}
+ICL_API int icl_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd, float* run_mean, float* run_var,
+                            int NB, int CH, long long S, float eps, float momentum, void* stream) {
+  bn_stats_k<<<CH, 512, 0, as_stream(stream)>>>(x, mean_rstd, run_mean, run_var, NB, CH, S, eps, momentum);
+  icl_count_launch(1);
+  const long long total = (long long)NB * CH * S;
+  bn_relu_apply_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, mean_rstd, gamma, beta, y, CH, S, total);
+  ICL_LAUNCHED("bn_relu_fwd");
+}
+// backward: g = dy * [y > 0];  dgamma = sum g*xh; dbeta = sum g; dx = gamma*rstd*(g - mean(g) - xh*mean(g*xh))
+__global__ void __launch_bounds__(512) bn_relu_bwd_reduce_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                                                            const float* __restrict__ mean_rstd, float* __restrict__ sums, int NB, int CH, long long S) {
+  __shared__ double red[66];
+  const int c = blockIdx.x;
+  const long long n = (long long)NB * S;
+  const float m = mean_rstd[2 * c], r = mean_rstd[2 * c + 1];
+  double a = 0.0, q = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const long long o = ((i / S) * CH + c) * S + (i % S);
+    const float g = y[o] > 0.f ? dy[o] : 0.f;
+    a += g; q += (double)g * ((x[o] - m) * r);
+  }
+  a = block_sum_d(a, red); q = block_sum_d(q, red + 33);
+  if (threadIdx.x == 0) { sums[2 * c] = (float)a; sums[2 * c + 1] = (float)q; }
+}
+__global__ void bn_relu_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
+                                    const float* __restrict__ mean_rstd, const float* __restrict__ g, const float* __restrict__ sums,
+                                    float* __restrict__ dx, int CH, long long S, long long total, float inv_n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)((i / S) % CH);
+    const float m = mean_rstd[2 * c], r = mean_rstd[2 * c + 1];
+    const float gg = y[i] > 0.f ? dy[i] : 0.f;
+    const float xh = (x[i] - m) * r;
+    dx[i] = g[c] * r * (gg - sums[2 * c] * inv_n - xh * sums[2 * c + 1] * inv_n);
+  }
+}
+ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums /*[CH,2]: dbeta,dgamma*/,
+                            float* dx, int NB, int CH, long long S, void* stream) {
+  bn_relu_bwd_reduce_k<<<CH, 512, 0, as_stream(stream)>>>(dy, x, y, mean_rstd, sums, NB, CH, S);
+  icl_count_launch(1);
+  const long long total = (long long)NB * CH * S;
+  bn_relu_bwd_apply_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dy, x, y, mean_rstd, gamma, sums, dx, CH, S, total,
+                                                                         1.f / (float)((long long)NB * S));
+  ICL_LAUNCHED("bn_relu_bwd");
+}
+
+// pointwise (1x1x1) weight gradient on planar maps: dw[o][i] = sum_{nb, s} dy[nb,o,s] * x[nb,i,s]; db[o] = sum dy
+__global__ void __launch_bounds__(256) planar_pw_wgrad_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
+                                                         float* __restrict__ db, int NB, int CO, int CI, long long S) {
+  __shared__ float red[33];
+  const int o = blockIdx.x / (CI + 1), i = blockIdx.x % (CI + 1);
+  float s = 0.f;
+  for (long long k = threadIdx.x; k < (long long)NB * S; k += blockDim.x) {
+    const long long nb = k / S, sp = k % S;
+    const float g = dy[(nb * CO + o) * S + sp];
+    s += (i < CI) ? g * x[(nb * CI + i) * S + sp] : g;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) {
+    if (i < CI) dw[o * CI + i] = s;
+    else if (db) db[o] = s;
+  }
+}
+ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, void* stream) {
+  planar_pw_wgrad_k<<<CO * (CI + 1), 256, 0, as_stream(stream)>>>(dy, x, dw, db, NB, CO, CI, S);
+  ICL_LAUNCHED("planar_pw_wgrad");
+}

@@ -1,0 +1,268 @@
+"""torch.autograd.Functions over the ICL-head kernels.
+
+Each Function is the CUDA replacement of one torch op class the reference dispatches inside
+InherentConsistent / Class_Decoder / Query_Attention / SeparableConv3d (networks/unet_3D_icl.py:155-345).
+Autograd composes them, so the reference's gradient pruning (dead uscl branches, detached targets) and its
+`.grad is None` set fall out of the graph structure exactly as they do for the reference.
+"""
+import torch
+
+from . import ops
+from .ops import P, c_f, c_int, c_ll, call
+
+
+def _c(t):
+    return t if t.is_contiguous() else t.contiguous()
+
+
+class LinearFn(torch.autograd.Function):
+    """y = act(x @ w.T + b) over the last axis (nn.Linear; also 1x1x1 Conv3d on NDHWC rows and Conv1d k=1)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, act):
+        ops._require_cuda(x)
+        x2 = _c(x.detach()).reshape(-1, x.shape[-1])
+        w_ = _c(w.detach())
+        y, pre = ops.linear_fwd(x2, w_, None if b is None else _c(b.detach()), act, want_pre=bool(act))
+        ctx.save_for_backward(x2, w_, pre if act else None)
+        ctx.has_bias, ctx.act, ctx.xshape = b is not None, act, x.shape
+        return y.reshape(x.shape[:-1] + (w.shape[0],))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w_, pre = ctx.saved_tensors
+        g = _c(dy).reshape(-1, w_.shape[0])
+        if ctx.act:
+            g = ops.gelu_bwd(g, pre)
+        dx = ops.linear_dgrad(g, w_).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
+        dw = db = None
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw, db = ops.linear_wgrad(g, x2, ctx.has_bias)
+        return dx, dw, db, None
+
+
+def linear(x, w, b=None, act=0):
+    return LinearFn.apply(x, w, b, act)
+
+
+class LayerNormFn(torch.autograd.Function):
+    """nn.LayerNorm over the last axis (C, or the spatial axis N for norm3; unet_3D_icl.py:187,248-258)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        ops._require_cuda(x)
+        C = x.shape[-1]
+        x2 = _c(x.detach()).reshape(-1, C)
+        rows = x2.shape[0]
+        y = torch.empty_like(x2)
+        mr = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+        call("icl_layernorm_fwd", P(x2), P(w.detach()), P(b.detach()), P(y), P(mr), c_ll(rows), c_int(C), c_f(eps))
+        ctx.save_for_backward(x2, w.detach(), mr)
+        ctx.xshape = x.shape
+        return y.reshape(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x2, w, mr = ctx.saved_tensors
+        C = x2.shape[1]
+        g = _c(dy).reshape(-1, C)
+        dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
+        want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
+        dw = torch.zeros((C,), dtype=torch.float32, device=g.device) if want_w else None
+        db = torch.zeros((C,), dtype=torch.float32, device=g.device) if want_w else None
+        call("icl_layernorm_bwd", P(g), P(x2), P(w), P(mr), P(dx), P(dw), P(db), c_ll(x2.shape[0]), c_int(C))
+        return (dx.reshape(ctx.xshape) if dx is not None else None), dw, db, None
+
+
+def layer_norm(x, w, b, eps=1e-5):
+    return LayerNormFn.apply(x, w, b, eps)
+
+
+class ProxyAttnFn(torch.autograd.Function):
+    """Query_Attention core (unet_3D_icl.py:287-296).  ql [B,K,C] is read flat as [B,H,K,hd]; kv [B,N,2C].
+    Returns (xv [B,K,C] flat view of softmax(map) @ v, map [B,K,H,N] = scaled logits BEFORE softmax)."""
+
+    @staticmethod
+    def forward(ctx, ql, kv, H, want_xv):
+        ops._require_cuda(ql)
+        ql_, kv_ = _c(ql.detach()), _c(kv.detach())
+        B, K, C = ql_.shape
+        N = kv_.shape[1]
+        scale = float(C // H) ** -0.5
+        amap = torch.empty((B, K, H, N), dtype=torch.float32, device=ql.device)
+        xv = torch.empty((B, K, C), dtype=torch.float32, device=ql.device) if want_xv else None
+        mstat = torch.empty((B * H * K, 2), dtype=torch.float32, device=ql.device) if want_xv else None
+        call("icl_proxy_attn_fwd", P(ql_), P(kv_), P(amap), P(xv), P(mstat), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K),
+             c_f(scale), c_int(1 if want_xv else 0))
+        ctx.save_for_backward(ql_, kv_, amap, mstat)
+        ctx.dims = (B, N, C, H, K, scale)
+        ctx.set_materialize_grads(False)
+        return xv, amap
+
+    @staticmethod
+    def backward(ctx, dxv, dmap):
+        ql_, kv_, amap, mstat = ctx.saved_tensors
+        B, N, C, H, K, scale = ctx.dims
+        if dxv is None and dmap is None:
+            return None, None, None, None
+        dl = torch.empty_like(amap)
+        dql = torch.empty_like(ql_)
+        dkv = torch.empty_like(kv_)
+        call("icl_proxy_attn_bwd", P(None if dmap is None else _c(dmap)), P(None if dxv is None else _c(dxv)), P(amap), P(ql_), P(kv_),
+             P(mstat), P(dl), P(dql), P(dkv), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K), c_f(scale))
+        return dql, dkv, None, None
+
+
+def proxy_attention(ql, kv, num_heads, want_xv=True):
+    return ProxyAttnFn.apply(ql, kv, num_heads, want_xv)
+
+
+class AddScaledFn(torch.autograd.Function):
+    """out = a + b * r  with r broadcast per leading-axis sample (DropPath residuals, unet_3D_icl.py:264-267);
+    r is None in eval mode."""
+
+    @staticmethod
+    def forward(ctx, a, b, r):
+        a_, b_ = _c(a.detach()), _c(b.detach())
+        rows = a_.shape[0]
+        out = ops.row_combine(a_, None, b_, r, rows)
+        ctx.r, ctx.rows = r, rows
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        g = _c(g)
+        db = g if ctx.r is None else ops.row_combine(g, ctx.r, None, None, ctx.rows)
+        return g, db, None
+
+
+def add_scaled(a, b, r=None):
+    return AddScaledFn.apply(a, b, r)
+
+
+class BatchMeanFn(torch.autograd.Function):
+    """x.mean(dim=0, keepdim=True) (updated_guided_Q.mean, unet_3D_icl.py:224)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        x_ = _c(x.detach())
+        B = x_.shape[0]
+        n = x_.numel() // B
+        out = torch.empty((1,) + tuple(x_.shape[1:]), dtype=torch.float32, device=x.device)
+        ones = torch.full((B,), 1.0 / B, dtype=torch.float32, device=x.device)
+        ops.sgemm(1, n, B, ones, B, 1, x_, n, 1, out, n, 1)
+        ctx.B = B
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return (g / ctx.B).expand((ctx.B,) + tuple(g.shape[1:]))
+
+
+def batch_mean(x):
+    return BatchMeanFn.apply(x)
+
+
+class DwConv3dFn(torch.autograd.Function):
+    """Depthwise 3x3x3 conv, groups = channels, no bias, on planar [NB, CH, d, h, w] (unet_3D_icl.py:321-323)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        x_, w_ = _c(x.detach()), _c(w.detach())
+        NB, CH, d, h, wd = x_.shape
+        y = torch.empty_like(x_)
+        call("icl_dwconv3d", P(x_), P(w_), P(y), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd), c_int(0))
+        ctx.save_for_backward(x_, w_)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_, w_ = ctx.saved_tensors
+        NB, CH, d, h, wd = x_.shape
+        dy = _c(dy)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_)
+            call("icl_dwconv3d", P(dy), P(w_), P(dx), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd), c_int(1))
+        dw = torch.empty_like(w_)
+        call("icl_dwconv3d_wgrad", P(x_), P(dy), P(dw), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd))
+        return dx, dw
+
+
+def dwconv3d(x, w):
+    return DwConv3dFn.apply(x, w)
+
+
+class BnReluFn(torch.autograd.Function):
+    """BatchNorm3d (training: batch statistics, running-stat update) + ReLU on planar [NB, CH, ...]
+    (bn_depth/relu1 and bn_point/relu2 of SeparableConv3d, unet_3D_icl.py:337-342)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, run_mean, run_var, training, momentum, eps):
+        x_ = _c(x.detach())
+        NB, CH = x_.shape[0], x_.shape[1]
+        S = x_.numel() // (NB * CH)
+        y = torch.empty_like(x_)
+        mr = torch.empty((CH, 2), dtype=torch.float32, device=x.device)
+        if training:
+            call("icl_bn_relu_fwd", P(x_), P(gamma.detach()), P(beta.detach()), P(y), P(mr), P(run_mean), P(run_var), c_int(NB), c_int(CH),
+                 c_ll(S), c_f(eps), c_f(momentum))
+        else:
+            raise RuntimeError("icl_b200 BatchNorm: eval-mode ICL heads are not on the reference's path "
+                               "(inference returns before the heads, unet_3D_icl.py:119-120)")
+        ctx.save_for_backward(x_, y, mr, gamma.detach())
+        ctx.dims = (NB, CH, S)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_, y, mr, gamma = ctx.saved_tensors
+        NB, CH, S = ctx.dims
+        sums = torch.empty((CH, 2), dtype=torch.float32, device=x_.device)
+        dx = torch.empty_like(x_)
+        call("icl_bn_relu_bwd", P(_c(dy)), P(x_), P(y), P(mr), P(gamma), P(sums), P(dx), c_int(NB), c_int(CH), c_ll(S))
+        return dx, sums[:, 1].contiguous(), sums[:, 0].contiguous(), None, None, None, None, None
+
+
+def bn_relu(x, bn, training):
+    if training and bn.num_batches_tracked is not None:
+        bn.num_batches_tracked += 1
+    return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps)
+
+
+class PlanarPointwiseFn(torch.autograd.Function):
+    """1x1x1 Conv3d on planar [NB, CI, S...] maps: y[nb] = W @ x[nb] (+ b)  (pointwise conv :325, attn_convs1 :196)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        x_ = _c(x.detach())
+        NB, CI = x_.shape[0], x_.shape[1]
+        S = x_.numel() // (NB * CI)
+        w2 = _c(w.detach()).reshape(w.shape[0], CI)
+        CO = w2.shape[0]
+        y = torch.empty((NB, CO) + tuple(x_.shape[2:]), dtype=torch.float32, device=x.device)
+        ops.sgemm(CO, S, CI, w2, CI, 1, x_, S, 1, y, S, 1, bias=None if b is None else b.detach(), bias_mode=2 if b is not None else 0,
+                  batch=NB, sA=0, sB=CI * S, sC=CO * S)
+        ctx.save_for_backward(x_, w2)
+        ctx.has_bias, ctx.wshape = b is not None, w.shape
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x_, w2 = ctx.saved_tensors
+        dy = _c(dy)
+        NB, CI = x_.shape[0], x_.shape[1]
+        CO = w2.shape[0]
+        S = x_.numel() // (NB * CI)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty_like(x_)
+            ops.sgemm(CI, S, CO, w2, 1, CI, dy, S, 1, dx, S, 1, batch=NB, sA=0, sB=CO * S, sC=CI * S)
+        dw = torch.empty_like(w2)
+        db = torch.empty((CO,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
+        call("icl_planar_pw_wgrad", P(dy), P(x_), P(dw), P(db), c_int(NB), c_int(CO), c_int(CI), c_ll(S))
+        return dx, dw.reshape(ctx.wshape), db
+
+
+def planar_pointwise(x, w, b=None):
+    return PlanarPointwiseFn.apply(x, w, b)

@@ -1,0 +1,100 @@
+"""Sliding-window inference — drop-in for test_single_case (reference test_3D_BraTS.py:79-142 ≡
+val_3D.test_single_case_base :15-82) and the Dice half of calculate_metric_percase (:175-187).
+
+Same window grid (last window clamped to the border), same x->y->z accumulation order, but the volume, the
+score map, the visit counts, the argmax and the Dice counts all stay on the device: one H2D of the volume and
+one D2H of the label map per case instead of one of each per window.  `rank`/`world_size` shard windows
+round-robin across processes; the caller sums score/cnt with an all-reduce.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import ops
+from .ops import P, c_int, c_ll, call
+
+
+def window_starts(size, patch, stride):
+    n = math.ceil((size - patch) / stride) + 1
+    return [min(stride * i, size - patch) for i in range(n)]
+
+
+def _accumulate(logits_ndhwc, score, cnt, xs, ys, zs):
+    """logits_ndhwc: [pw, ph, pd, K] (one window, channels-last)."""
+    pw, ph, pd, K = logits_ndhwc.shape
+    _, W, H, D = score.shape
+    call("icl_sw_accumulate", P(logits_ndhwc), c_int(K), c_int(pw), c_int(ph), c_int(pd), P(score), P(cnt), c_int(W), c_int(H), c_int(D),
+         c_int(xs), c_int(ys), c_int(zs))
+
+
+def _finalize(score, cnt):
+    K = score.shape[0]
+    S = cnt.numel()
+    label = torch.empty(cnt.shape, dtype=torch.int64, device=score.device)
+    call("icl_sw_finalize", P(score), P(cnt), c_int(K), c_ll(S), P(label))
+    return label
+
+
+def sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=0, world_size=1, inference_kw=False):
+    """Returns (score [K,ww,hh,dd], cnt [ww,hh,dd], pads) for this rank's share of the windows."""
+    dev = next(net.parameters()).device
+    if dev.type != "cuda":
+        raise RuntimeError("icl_b200 inference runs on CUDA only (no CPU fallback)")
+    img = torch.as_tensor(np.asarray(image), dtype=torch.float32)
+    w, h, d = img.shape
+    pads = []
+    for s, p in zip((w, h, d), patch_size):
+        tot = max(p - s, 0)
+        pads.append((tot // 2, tot - tot // 2))
+    img = img.to(dev, non_blocking=True)
+    if any(a + b > 0 for a, b in pads):
+        img = torch.nn.functional.pad(img, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
+    ww, hh, dd = img.shape
+    px, py, pz = patch_size
+    score = torch.zeros((num_classes, ww, hh, dd), dtype=torch.float32, device=dev)
+    cnt = torch.zeros((ww, hh, dd), dtype=torch.float32, device=dev)
+    n = 0
+    with torch.no_grad():
+        for xs in window_starts(ww, px, stride_xy):
+            for ys in window_starts(hh, py, stride_xy):
+                for zs in window_starts(dd, pz, stride_z):
+                    mine = (n % world_size) == rank
+                    n += 1
+                    if not mine:
+                        continue
+                    patch = img[xs:xs + px, ys:ys + py, zs:zs + pz].contiguous()[None, None]
+                    y1 = net(patch, inference=True) if inference_kw else net(patch)
+                    _accumulate(ops.to_ndhwc(y1)[0], score, cnt, xs, ys, zs)
+    return score, cnt, pads
+
+
+def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, inference_kw=False):
+    """numpy [w,h,d] in -> numpy int64 label map out (host-blocking, like the reference)."""
+    w, h, d = np.asarray(image).shape
+    score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, inference_kw=inference_kw)
+    label = _finalize(score, cnt)
+    label = label[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
+    return label.cpu().numpy()
+
+
+test_single_case.__test__ = False  # not a pytest test
+
+
+def dice_metric(pred, gt):
+    """Dice of (pred>0) vs (gt>0) with exact integer counts; the empty-set conventions of
+    calculate_metric_percase (test_3D_BraTS.py:175-187).  Returns (dice, (|A∩B|, |A|, |B|))."""
+    p = torch.as_tensor(pred).long().contiguous()
+    g = torch.as_tensor(gt).long().contiguous()
+    if not (p.is_cuda and g.is_cuda):
+        raise RuntimeError("icl_b200.inference.dice_metric runs on CUDA tensors only")
+    counts = torch.zeros((3,), dtype=torch.int64, device=p.device)
+    call("icl_dice_counts", P(p), P(g), c_ll(p.numel()), P(counts))
+    inter, na, nb = (int(v) for v in counts.cpu())
+    if na > 0 and nb > 0:
+        dice = 2.0 * inter / float(na + nb)
+    elif na == 0 and nb == 0:
+        dice = 1.0
+    else:
+        dice = 0.0
+    return dice, (inter, na, nb)

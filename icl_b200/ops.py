@@ -1,0 +1,252 @@
+"""Thin Python wrappers over the C-ABI kernels (include/icl_b200.h).
+
+Internal activation formats:
+  NDHWC : contiguous float tensor [B, D, H, W, C]            (F32CL in the header)
+  PK    : contiguous bf16 tensor  [P, B, C/8, D, H, W, 8]    (split hi/lo tensor-core operand)
+At the module boundary NDHWC tensors are exposed as [B, C, D, H, W] views (channels_last_3d).
+"""
+import ctypes
+import os
+
+import torch
+
+from . import _lib
+from .precision import planes
+
+c_int, c_ll, c_f, c_d, c_ull = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong
+P = _lib.ptr
+call = _lib.call
+
+
+def _require_cuda(t):
+    if not t.is_cuda:
+        raise RuntimeError("icl_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
+
+
+def to_ndhwc(x):
+    """[B,C,D,H,W] (any strides) -> contiguous [B,D,H,W,C] float32 (no copy if already channels-last)."""
+    _require_cuda(x)
+    if x.dtype != torch.float32:
+        x = x.float()
+    return x.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def to_ncdhw_view(x):
+    """contiguous [B,D,H,W,C] -> [B,C,D,H,W] view."""
+    return x.permute(0, 4, 1, 2, 3)
+
+
+def empty_pk(B, C, D, H, W, device):
+    return torch.empty((planes(), B, C // 8, D, H, W, 8), dtype=torch.bfloat16, device=device)
+
+
+def pk_ok(C):
+    return C % 16 == 0
+
+
+# ------------------------------------------------------------------------------------------
+# conv 3x3x3
+# ------------------------------------------------------------------------------------------
+
+def umma_ok(cins, cout):
+    """Shapes the tcgen05 implicit-GEMM kernel takes; everything else runs the fp32 CUDA-core kernel.
+    ICL_DISABLE_UMMA=1 is a debugging knob that routes every conv to the CUDA-core kernel."""
+    if os.environ.get("ICL_DISABLE_UMMA") == "1":
+        return False
+    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and cout <= 256
+
+
+_MAX_CTAS = 0  # 0 = one CTA per SM; tests may lower it to exercise the persistent tile loop
+
+
+def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, out=None):
+    """pks: 1 or 2 PK tensors (virtual channel concat).  Returns NDHWC output [B,D,H,W,cout], or a pair
+    (y0 [..,split], y1 [..,cout-split]) when split is given (data gradient of a concatenated input)."""
+    dev = pks[0].device
+    if split is None:
+        y0 = out if out is not None else torch.empty((B, D, H, W, cout), dtype=torch.float32, device=dev)
+        y1, ld1, sp = None, 0, 0
+    else:
+        y0 = torch.empty((B, D, H, W, split), dtype=torch.float32, device=dev)
+        y1 = torch.empty((B, D, H, W, cout - split), dtype=torch.float32, device=dev)
+        ld1, sp = cout - split, split
+    pk1 = pks[1] if len(pks) > 1 else None
+    c1 = cins[1] if len(cins) > 1 else 0
+    call("icl_conv3d_umma_fwd", P(pks[0]), c_int(cins[0]), P(pk1), c_int(c1), P(wp), P(bias), P(y0), c_int(y0.shape[-1]), P(y1),
+         c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), c_int(planes()), c_int(_MAX_CTAS))
+    return y0 if split is None else (y0, y1)
+
+
+def pack_w_umma(w, dgrad):
+    """torch conv weight [Cout,Cin,3,3,3] -> staged bf16 operand (see conv3d_umma.cu)."""
+    cout, cin = w.shape[0], w.shape[1]
+    n = cin if dgrad else cout
+    nt = _lib.lib().icl_umma_ntile(n)
+    wp = torch.empty(planes() * n * (cout if dgrad else cin) * 27, dtype=torch.bfloat16, device=w.device)
+    call("icl_pack_w_umma", P(w), P(wp), c_int(cout), c_int(cin), c_int(1 if dgrad else 0), c_int(nt), c_int(planes()))
+    return wp
+
+
+def repack_w_f32(w, dgrad):
+    cout, cin = w.shape[0], w.shape[1]
+    wp = torch.empty(27 * cin * cout, dtype=torch.float32, device=w.device)
+    call("icl_repack_w_f32", P(w), P(wp), c_int(cout), c_int(cin), c_int(1 if dgrad else 0))
+    return wp
+
+
+def conv3d_direct(xs, cins, wp, bias, cout, B, D, H, W, stats=None):
+    y = torch.empty((B, D, H, W, cout), dtype=torch.float32, device=xs[0].device)
+    x1 = xs[1] if len(xs) > 1 else None
+    c1 = cins[1] if len(cins) > 1 else 0
+    call("icl_conv3d_direct_fwd", P(xs[0]), c_int(cins[0]), P(x1), c_int(c1), P(wp), P(bias), P(y), c_int(cout), c_int(0), P(stats),
+         c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout))
+    return y
+
+
+def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
+    """Returns (dw [Cout, sum(cins), 3,3,3], dbias [Cout] or None)."""
+    cin_total = sum(cins)
+    dw = torch.zeros((cout, cin_total, 3, 3, 3), dtype=torch.float32, device=dy.device)
+    db = torch.zeros((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    off = 0
+    for i, (x, c) in enumerate(zip(xs, cins)):
+        call("icl_conv3d_wgrad", P(x), c_int(c), P(dy), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(db if i == 0 else None),
+             c_int(B), c_int(D), c_int(H), c_int(W))
+        off += c
+    return dw, db
+
+
+# ------------------------------------------------------------------------------------------
+# InstanceNorm + ReLU, pool, upsample, dropout
+# ------------------------------------------------------------------------------------------
+
+def instnorm_finalize(stats, B, C, S, eps=1e-5):
+    mr = torch.empty((B, C, 2), dtype=torch.float32, device=stats.device)
+    call("icl_instnorm_finalize", P(stats), P(mr), c_int(B), c_int(C), c_ll(S), c_f(eps))
+    return mr
+
+
+def instnorm_relu_fwd(y, mr, want_pk):
+    B, D, H, W, C = y.shape
+    a = torch.empty_like(y)
+    pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
+    call("icl_instnorm_relu_fwd", P(y), P(mr), P(a), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_ll(D * H * W))
+    return a, pk
+
+
+def instnorm_relu_bwd(dA, y, mr, want_pk):
+    B, D, H, W, C = y.shape
+    red = torch.zeros((B, C, 2), dtype=torch.float64, device=y.device)
+    dY = torch.empty_like(y)
+    pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
+    call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C),
+         c_ll(D * H * W))
+    return dY, pk
+
+
+def pack_pk(x):
+    B, D, H, W, C = x.shape
+    pk = empty_pk(B, C, D, H, W, x.device)
+    call("icl_pack_pk", P(x), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_ll(D * H * W))
+    return pk
+
+
+def maxpool_fwd(a, want_pk):
+    B, D, H, W, C = a.shape
+    out = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.float32, device=a.device)
+    idx = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.uint8, device=a.device)
+    pk = empty_pk(B, C, D // 2, H // 2, W // 2, a.device) if want_pk else None
+    call("icl_maxpool3d_fwd", P(a), P(out), P(idx), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_int(D), c_int(H), c_int(W))
+    return out, idx, pk
+
+
+def maxpool_bwd(dout, idx, dx, accumulate):
+    B, D, H, W, C = dx.shape
+    call("icl_maxpool3d_bwd", P(dout), P(idx), P(dx), c_int(1 if accumulate else 0), c_int(B), c_int(C), c_int(D), c_int(H), c_int(W))
+
+
+def upsample2x_fwd(x, want_pk):
+    B, d, h, w, C = x.shape
+    out = torch.empty((B, 2 * d, 2 * h, 2 * w, C), dtype=torch.float32, device=x.device)
+    pk = empty_pk(B, C, 2 * d, 2 * h, 2 * w, x.device) if want_pk else None
+    call("icl_upsample2x_fwd", P(x), P(out), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_int(d), c_int(h), c_int(w))
+    return out, pk
+
+
+def upsample2x_bwd(dout, c_off, C, dx, accumulate):
+    """dout: NDHWC fine-res gradient with dout.shape[-1] channels, this op owns [c_off, c_off+C)."""
+    B, d, h, w, _ = dx.shape
+    call("icl_upsample2x_bwd", P(dout), c_int(dout.shape[-1]), c_int(c_off), P(dx), c_int(1 if accumulate else 0), c_int(B), c_int(C),
+         c_int(d), c_int(h), c_int(w))
+
+
+def dropout(x, p, mask=None, seed=0):
+    out = torch.empty_like(x)
+    call("icl_dropout", P(x), P(out), P(mask), c_ull(int(seed) & 0xFFFFFFFFFFFFFFFF), c_f(p), c_ll(x.numel()))
+    return out
+
+
+# ------------------------------------------------------------------------------------------
+# GEMM family
+# ------------------------------------------------------------------------------------------
+
+def sgemm(M, N, K, A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias=None, bias_mode=0, act=0, accumulate=False, pre=None, batch=1, sA=0, sB=0,
+          sC=0):
+    call("icl_sgemm", c_int(M), c_int(N), c_int(K), P(A), c_ll(sam), c_ll(sak), c_ll(sA), P(Bm), c_ll(sbk), c_ll(sbn), c_ll(sB), P(C),
+         c_ll(scm), c_ll(scn), c_ll(sC), c_int(batch), P(bias), c_int(bias_mode), c_int(act), c_int(1 if accumulate else 0), P(pre))
+
+
+def linear_fwd(x2d, w, b, act=0, want_pre=False):
+    """y = act(x2d @ w.T + b); x2d [M,K] contiguous, w [N,K]."""
+    M, K = x2d.shape
+    N = w.shape[0]
+    y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
+    pre = torch.empty_like(y) if want_pre else None
+    if M <= 16 and K >= 1024:
+        call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act))
+    else:
+        sgemm(M, N, K, x2d, K, 1, w, 1, K, y, N, 1, bias=b, bias_mode=1 if b is not None else 0, act=act, pre=pre)
+    return y, pre
+
+
+def linear_dgrad(dy2d, w):
+    M, N = dy2d.shape
+    K = w.shape[1]
+    if M <= 16 and N >= 1024 and K % 4 == 0:
+        dx = torch.zeros((M, K), dtype=torch.float32, device=dy2d.device)
+        call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx))
+    else:
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy2d.device)
+        sgemm(M, K, N, dy2d, N, 1, w, K, 1, dx, K, 1)
+    return dx
+
+
+def linear_wgrad(dy2d, x2d, want_bias=True):
+    """dW [N,K] = dy^T x ; db [N] = colsum(dy)."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    dW = torch.empty((N, K), dtype=torch.float32, device=dy2d.device)
+    db = torch.empty((N,), dtype=torch.float32, device=dy2d.device) if want_bias else None
+    if M <= 64 and N * K >= (1 << 20):
+        call("icl_outer_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(db), c_int(0))
+    else:
+        sgemm(N, K, M, dy2d, 1, N, x2d, K, 1, dW, K, 1)
+        if want_bias:
+            call("icl_colsum", P(dy2d), P(db), c_ll(M), c_int(N), c_int(0))
+    return dW, db
+
+
+def gelu_bwd(dy, pre):
+    dx = torch.empty_like(pre)
+    call("icl_gelu_bwd", P(dy), P(pre), P(dx), c_ll(pre.numel()))
+    return dx
+
+
+def axpby(x, y, alpha, beta):
+    call("icl_axpby", P(x), P(y), c_f(alpha), c_f(beta), c_ll(x.numel()))
+
+
+def row_combine(a, sa, b, sb, rows):
+    out = torch.empty_like(a)
+    call("icl_row_combine", P(a), P(sa), P(b), P(sb), P(out), c_ll(rows), c_ll(a.numel() // rows))
+    return out

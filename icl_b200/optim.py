@@ -1,0 +1,67 @@
+"""Fused multi-tensor SGD — drop-in for `optim.SGD(model.parameters(), lr, momentum=0.9, weight_decay=1e-4)`
+as used by the ICL loops (train_inherent_consistent_unet_3D_BraTS.py:85-86,113-119).
+
+Same update rule as torch.optim.SGD (dampening 0, no nesterov); parameters whose .grad is None are skipped
+entirely (no weight decay, no momentum) exactly like torch.  One kernel launch per param group per step
+(the 785 M-parameter model is otherwise ~230 launches), lr read from device memory.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from .ops import P, c_f, c_int, call
+
+
+class SGD(torch.optim.Optimizer):
+    def __init__(self, params, lr=0.01, momentum=0.0, dampening=0, weight_decay=0.0, nesterov=False):
+        if dampening != 0 or nesterov:
+            raise NotImplementedError("icl_b200.optim.SGD implements dampening=0, nesterov=False (the ICL loops' configuration)")
+        super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self._chunk = _lib.lib().icl_sgd_chunk()
+        self._cache = {}
+
+    def _chunks(self, numels, device):
+        key = (tuple(numels), str(device))
+        hit = self._cache.get(key)
+        if hit is None:
+            ct, co = [], []
+            for i, n in enumerate(numels):
+                offs = np.arange(0, n, self._chunk, dtype=np.int64)
+                ct.append(np.full(offs.shape, i, dtype=np.int32))
+                co.append(offs)
+            ct = torch.from_numpy(np.concatenate(ct)).to(device)
+            co = torch.from_numpy(np.concatenate(co)).to(device)
+            hit = (ct, co)
+            self._cache = {key: hit}
+        return hit
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        for group in self.param_groups:
+            rows, keep = [], []
+            for p in group["params"]:
+                if p.grad is None:
+                    continue
+                if not p.is_cuda or p.dtype != torch.float32 or not p.is_contiguous():
+                    raise RuntimeError("icl_b200.optim.SGD needs contiguous float32 CUDA parameters (no CPU fallback)")
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                st = self.state[p]
+                if "momentum_buffer" not in st:
+                    st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+                m = st["momentum_buffer"]
+                rows.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel()))
+                keep.append(g)
+            if not rows:
+                continue
+            dev = group["params"][0].device
+            tab = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(dev)
+            ct, co = self._chunks([r[3] for r in rows], dev)
+            lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+            with torch.cuda.device(dev):
+                call("icl_sgd_multi", P(tab), P(ct), P(co), c_int(ct.numel()), P(lr), c_f(group["momentum"]), c_f(group["weight_decay"]),
+                     c_int(0))
+        return loss
