@@ -73,12 +73,49 @@ def stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-def call(name, *args):
-    """Invoke an int-returning entry point on the current stream; raise on failure."""
+_PROFILE = None  # list of (name, start_event, end_event, gflop, mbytes) while profiling
+
+
+def call(name, *args, gflop=0.0, mbytes=0.0):
+    """Invoke an int-returning entry point on the current stream; raise on failure.
+    gflop / mbytes: algorithmic work of this launch, recorded only while profiling (bench.py roofline)."""
     l = lib()
-    rc = getattr(l, name)(*args, stream())
+    if _PROFILE is not None:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = getattr(l, name)(*args, stream())
+        e1.record()
+        _PROFILE.append((name, e0, e1, gflop, mbytes))
+    else:
+        rc = getattr(l, name)(*args, stream())
     if rc != 0:
         raise RuntimeError("icl_b200.%s failed (%d): %s" % (name, rc, l.icl_last_error().decode()))
+
+
+def profile_start():
+    global _PROFILE
+    _PROFILE = []
+
+
+def profile_stop(n_steps=1):
+    """Aggregate per entry point: CUDA-event time on the launching stream, launches, algorithmic GFLOP / MB."""
+    global _PROFILE
+    rec, _PROFILE = _PROFILE, None
+    torch.cuda.synchronize()
+    agg = {}
+    for name, e0, e1, gf, mb in rec:
+        a = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
+        a[0] += e0.elapsed_time(e1)
+        a[1] += 1
+        a[2] += gf
+        a[3] += mb
+    total = sum(a[0] for a in agg.values()) or 1.0
+    ks = []
+    for name, (ms, n, gf, mb) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
+        ks.append({"name": name, "ms_per_step": ms / n_steps, "launches_per_step": n / n_steps, "share": ms / total,
+                   "ms_per_launch": ms / n, "gflop_per_launch": gf / n, "mbytes_per_launch": mb / n,
+                   "tflops": (gf / ms) if ms and gf else None, "gbs": (mb / ms) if ms and mb else None})
+    return {"kernels": ks, "kernel_ms_per_step": total / n_steps}
 
 
 def launch_count():

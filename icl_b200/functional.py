@@ -7,7 +7,7 @@ Autograd composes them, so the reference's gradient pruning (dead uscl branches,
 """
 import torch
 
-from . import ops
+from . import ops, parallel
 from .ops import P, c_f, c_int, c_ll, call
 
 
@@ -25,7 +25,7 @@ class LinearFn(torch.autograd.Function):
         w_ = _c(w.detach())
         y, pre = ops.linear_fwd(x2, w_, None if b is None else _c(b.detach()), act, want_pre=bool(act))
         ctx.save_for_backward(x2, w_, pre if act else None)
-        ctx.has_bias, ctx.act, ctx.xshape = b is not None, act, x.shape
+        ctx.has_bias, ctx.act, ctx.xshape, ctx.w_id = b is not None, act, x.shape, id(w)
         return y.reshape(x.shape[:-1] + (w.shape[0],))
 
     @staticmethod
@@ -37,7 +37,15 @@ class LinearFn(torch.autograd.Function):
         dx = ops.linear_dgrad(g, w_).reshape(ctx.xshape) if ctx.needs_input_grad[0] else None
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw, db = ops.linear_wgrad(g, x2, ctx.has_bias)
+            dp = parallel.factor_context()
+            if dp["world"] > 1 and ctx.w_id in dp["factored_ids"]:
+                # data parallel: exchange the rank-<=rows factors instead of all-reducing the 764 MB dW
+                dw = parallel.averaged_factored_wgrad(g, x2, ops.outer_wgrad_acc, dp["group"])
+                if ctx.has_bias:
+                    db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
+                    call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))
+            else:
+                dw, db = ops.linear_wgrad(g, x2, ctx.has_bias)
         return dx, dw, db, None
 
 

@@ -16,6 +16,7 @@ from .precision import planes
 c_int, c_ll, c_f, c_d, c_ull = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong
 P = _lib.ptr
 call = _lib.call
+profile_start, profile_stop = _lib.profile_start, _lib.profile_stop
 
 
 def _require_cuda(t):
@@ -73,7 +74,8 @@ def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, o
     pk1 = pks[1] if len(pks) > 1 else None
     c1 = cins[1] if len(cins) > 1 else 0
     call("icl_conv3d_umma_fwd", P(pks[0]), c_int(cins[0]), P(pk1), c_int(c1), P(wp), P(bias), P(y0), c_int(y0.shape[-1]), P(y1),
-         c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), c_int(planes()), c_int(_MAX_CTAS))
+         c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), c_int(planes()), c_int(_MAX_CTAS),
+         gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W)
     return y0 if split is None else (y0, y1)
 
 
@@ -99,7 +101,7 @@ def conv3d_direct(xs, cins, wp, bias, cout, B, D, H, W, stats=None):
     x1 = xs[1] if len(xs) > 1 else None
     c1 = cins[1] if len(cins) > 1 else 0
     call("icl_conv3d_direct_fwd", P(xs[0]), c_int(cins[0]), P(x1), c_int(c1), P(wp), P(bias), P(y), c_int(cout), c_int(0), P(stats),
-         c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout))
+         c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W)
     return y
 
 
@@ -111,7 +113,7 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     off = 0
     for i, (x, c) in enumerate(zip(xs, cins)):
         call("icl_conv3d_wgrad", P(x), c_int(c), P(dy), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(db if i == 0 else None),
-             c_int(B), c_int(D), c_int(H), c_int(W))
+             c_int(B), c_int(D), c_int(H), c_int(W), gflop=2e-9 * 27 * c * cout * B * D * H * W)
         off += c
     return dw, db
 
@@ -130,7 +132,8 @@ def instnorm_relu_fwd(y, mr, want_pk):
     B, D, H, W, C = y.shape
     a = torch.empty_like(y)
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
-    call("icl_instnorm_relu_fwd", P(y), P(mr), P(a), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_ll(D * H * W))
+    call("icl_instnorm_relu_fwd", P(y), P(mr), P(a), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_ll(D * H * W),
+         mbytes=1e-6 * y.numel() * (8 + (2 * planes() if want_pk else 0)))
     return a, pk
 
 
@@ -140,7 +143,7 @@ def instnorm_relu_bwd(dA, y, mr, want_pk):
     dY = torch.empty_like(y)
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
     call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C),
-         c_ll(D * H * W))
+         c_ll(D * H * W), mbytes=1e-6 * y.numel() * (20 + (2 * planes() if want_pk else 0)))
     return dY, pk
 
 
@@ -203,7 +206,8 @@ def linear_fwd(x2d, w, b, act=0, want_pre=False):
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     pre = torch.empty_like(y) if want_pre else None
     if M <= 16 and K >= 1024:
-        call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act))
+        call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act),
+             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K)
     else:
         sgemm(M, N, K, x2d, K, 1, w, 1, K, y, N, 1, bias=b, bias_mode=1 if b is not None else 0, act=act, pre=pre)
     return y, pre
@@ -214,7 +218,8 @@ def linear_dgrad(dy2d, w):
     K = w.shape[1]
     if M <= 16 and N >= 1024 and K % 4 == 0:
         dx = torch.zeros((M, K), dtype=torch.float32, device=dy2d.device)
-        call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx))
+        call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), mbytes=4e-6 * (N * K + M * K + M * N),
+             gflop=2e-9 * M * N * K)
     else:
         dx = torch.empty((M, K), dtype=torch.float32, device=dy2d.device)
         sgemm(M, K, N, dy2d, N, 1, w, K, 1, dx, K, 1)
@@ -228,12 +233,25 @@ def linear_wgrad(dy2d, x2d, want_bias=True):
     dW = torch.empty((N, K), dtype=torch.float32, device=dy2d.device)
     db = torch.empty((N,), dtype=torch.float32, device=dy2d.device) if want_bias else None
     if M <= 64 and N * K >= (1 << 20):
-        call("icl_outer_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(db), c_int(0))
+        call("icl_outer_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(db), c_int(0),
+             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K)
     else:
         sgemm(N, K, M, dy2d, 1, N, x2d, K, 1, dW, K, 1)
         if want_bias:
             call("icl_colsum", P(dy2d), P(db), c_ll(M), c_int(N), c_int(0))
     return dW, db
+
+
+def outer_wgrad_acc(dy2d, x2d, dW):
+    """dW (+)= dy^T x for <= 64 rows (factor-exchange data parallelism, icl_b200/parallel.py)."""
+    M, N = dy2d.shape
+    K = x2d.shape[1]
+    acc = dW is not None
+    if dW is None:
+        dW = torch.empty((N, K), dtype=torch.float32, device=dy2d.device)
+    call("icl_outer_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(None), c_int(1 if acc else 0),
+         mbytes=4e-6 * N * K * (2 if acc else 1))
+    return dW
 
 
 def gelu_bwd(dy, pre):

@@ -63,5 +63,5 @@ class SGD(torch.optim.Optimizer):
             lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
                 call("icl_sgd_multi", P(tab), P(ct), P(co), c_int(ct.numel()), P(lr), c_f(group["momentum"]), c_f(group["weight_decay"]),
-                     c_int(0))
+                     c_int(0), mbytes=20e-6 * sum(r[3] for r in rows))
         return loss

@@ -150,6 +150,12 @@ def test_full_step_golden(name):
     for k, p in net.named_parameters():
         if p.grad is None:
             continue
+        if k.endswith(".0.bias") and "sspa" not in k and "uscl" not in k:
+            # conv bias in front of InstanceNorm: the gradient is mathematically zero; both sides hold only
+            # rounding noise (reference l2 ~1e-5), so compare against an absolute bound instead of each other
+            if p.grad.norm().item() > 1e-3 or float(g["gsum/" + k][1]) > 1e-3:
+                bad.append("%s: zero-gradient bias has l2 %.3e (ref %.3e)" % (k, p.grad.norm().item(), float(g["gsum/" + k][1])))
+            continue
         try:
             check_summary(p.grad, g["gsum/" + k], g["gval/" + k], 5e-3, k, abs_floor=5e-6)
         except AssertionError as e:

@@ -261,7 +261,7 @@ def test_proxy_attention(B, N, C, H, K):
     map_ref = logits.permute(0, 2, 1, 3)
     dxv = torch.randn(B, K, C, generator=g(3))
     dmap = torch.randn(B, K, H, N, generator=g(4))
-    gq, gkv = torch.autograd.grad((xv_ref, map_ref), (ql, kv), (dxv, dmap))
+    gq, gkv = torch.autograd.grad((xv_ref, map_ref), (ql, kv), (dxv, dmap), retain_graph=True)
     qc, kc = ql.detach().cuda().requires_grad_(True), kv.detach().cuda().requires_grad_(True)
     xv, amap = Fn.proxy_attention(qc, kc, H)
     torch.autograd.backward((xv, amap), (dxv.cuda(), dmap.cuda()))

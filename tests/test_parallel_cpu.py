@@ -1,0 +1,71 @@
+"""CPU, world_size-2 gloo: the data-parallel exchange of icl_b200/parallel.py — bucketed all-reduce of the normal
+gradients and the factor all-gather that replaces the 3 GB mlp2 gradient all-reduce.  Parity
+definition: the R-rank result equals the mean of the R single-process gradients."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from icl_b200 import parallel
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+    unused = torch.nn.Parameter(torch.zeros(3))
+    model.register_parameter("unused", unused)
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in model.parameters():
+        if p is not unused:
+            p.grad = torch.randn(p.shape, generator=g)
+    avg = parallel.GradAverager(model, world)
+    avg.average()
+    grads = {k: (None if p.grad is None else p.grad.clone()) for k, p in model.named_parameters()}
+    # factor exchange: dW_mean == mean_r dy_r^T x_r
+    dy = torch.randn(5, 6, generator=g)
+    x = torch.randn(5, 7, generator=g)
+
+    def wgrad(dy_, x_, acc):
+        d = dy_.t() @ x_
+        return d if acc is None else acc + d
+    dW = parallel.averaged_factored_wgrad(dy, x, wgrad)
+    q.put((rank, grads, dy, x, dW))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_grad_averager_and_factor_exchange_gloo():
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # expected: mean of the two ranks' local gradients
+    exp = []
+    for rank in range(world):
+        g = torch.Generator().manual_seed(100 + rank)
+        torch.manual_seed(0)
+        model = torch.nn.Sequential(torch.nn.Linear(8, 8), torch.nn.Linear(8, 4))
+        model.register_parameter("unused", torch.nn.Parameter(torch.zeros(3)))
+        exp.append({k: torch.randn(p.shape, generator=g) for k, p in model.named_parameters() if k != "unused"})
+    for rank in range(world):
+        grads = res[rank][1]
+        assert grads["unused"] is None  # a parameter without gradient stays None on every rank
+        for k in exp[0]:
+            assert torch.allclose(grads[k], (exp[0][k] + exp[1][k]) / 2, atol=1e-6), k
+    want_dW = sum(r[2].t() @ r[3] for r in res) / world
+    for r in res:
+        assert torch.allclose(r[4], want_dW, atol=1e-5)
