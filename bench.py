@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--detail", default="", help="write the per-(kernel, shape) CUDA-event breakdown to this JSON file")
     return ap.parse_args()
 
 
@@ -257,6 +258,9 @@ def main_gpu(a):
             step(x_dev, y_dev)
         torch.cuda.synchronize()
         prof = ops.profile_stop(nprof)
+        if a.detail:
+            os.makedirs(os.path.dirname(os.path.abspath(a.detail)), exist_ok=True)
+            json.dump(prof["detail"], open(a.detail, "w"), indent=1)
 
     cpu = None
     if rank == 0 and world == 1 and not a.no_cpu_baseline:

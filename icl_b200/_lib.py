@@ -76,7 +76,7 @@ def stream():
 _PROFILE = None  # list of (name, start_event, end_event, gflop, mbytes) while profiling
 
 
-def call(name, *args, gflop=0.0, mbytes=0.0):
+def call(name, *args, gflop=0.0, mbytes=0.0, tag=""):
     """Invoke an int-returning entry point on the current stream; raise on failure.
     gflop / mbytes: algorithmic work of this launch, recorded only while profiling (bench.py roofline)."""
     l = lib()
@@ -85,7 +85,7 @@ def call(name, *args, gflop=0.0, mbytes=0.0):
         e0.record()
         rc = getattr(l, name)(*args, stream())
         e1.record()
-        _PROFILE.append((name, e0, e1, gflop, mbytes))
+        _PROFILE.append((name, e0, e1, gflop, mbytes, tag))
     else:
         rc = getattr(l, name)(*args, stream())
     if rc != 0:
@@ -103,19 +103,24 @@ def profile_stop(n_steps=1):
     rec, _PROFILE = _PROFILE, None
     torch.cuda.synchronize()
     agg = {}
-    for name, e0, e1, gf, mb in rec:
-        a = agg.setdefault(name, [0.0, 0, 0.0, 0.0])
-        a[0] += e0.elapsed_time(e1)
-        a[1] += 1
-        a[2] += gf
-        a[3] += mb
+    detail = {}
+    for name, e0, e1, gf, mb, tag in rec:
+        t = e0.elapsed_time(e1)
+        for d, key in ((agg, name), (detail, name + ("[%s]" % tag if tag else ""))):
+            a = d.setdefault(key, [0.0, 0, 0.0, 0.0])
+            a[0] += t
+            a[1] += 1
+            a[2] += gf
+            a[3] += mb
     total = sum(a[0] for a in agg.values()) or 1.0
     ks = []
     for name, (ms, n, gf, mb) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
         ks.append({"name": name, "ms_per_step": ms / n_steps, "launches_per_step": n / n_steps, "share": ms / total,
                    "ms_per_launch": ms / n, "gflop_per_launch": gf / n, "mbytes_per_launch": mb / n,
                    "tflops": (gf / ms) if ms and gf else None, "gbs": (mb / ms) if ms and mb else None})
-    return {"kernels": ks, "kernel_ms_per_step": total / n_steps}
+    det = [{"name": k, "ms_per_step": v[0] / n_steps, "launches_per_step": v[1] / n_steps, "gflop_per_launch": v[2] / v[1],
+            "mbytes_per_launch": v[3] / v[1]} for k, v in sorted(detail.items(), key=lambda kv: -kv[1][0])]
+    return {"kernels": ks, "kernel_ms_per_step": total / n_steps, "detail": det}
 
 
 def launch_count():

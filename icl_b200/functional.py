@@ -43,7 +43,7 @@ class LinearFn(torch.autograd.Function):
                 dw = parallel.averaged_factored_wgrad(g, x2, ops.outer_wgrad_acc, dp["group"])
                 if ctx.has_bias:
                     db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
-                    call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))
+                    call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0), tag="%dx%d" % (g.shape[0], w_.shape[0]))
             else:
                 dw, db = ops.linear_wgrad(g, x2, ctx.has_bias)
         return dx, dw, db, None

@@ -185,7 +185,7 @@ class Backbone3DFn(torch.autograd.Function):
             dwf = torch.empty((K, C1), dtype=torch.float32, device=gf.device)
             ops.sgemm(K, C1, rows, gf, 1, K, rec["up1d"], C1, 1, dwf, C1, 1)
             dbf = torch.empty((K,), dtype=torch.float32, device=gf.device)
-            ops.call("icl_colsum", ops.P(gf), ops.P(dbf), ops.c_ll(rows), ops.c_int(K), ops.c_int(0))
+            ops.call("icl_colsum", ops.P(gf), ops.P(dbf), ops.c_ll(rows), ops.c_int(K), ops.c_int(0), tag="%dx%d" % (rows, K))
             grads["final"] = [dwf.reshape(K, C1, 1, 1, 1), dbf]
             if drop_cfg is not None:
                 d_up1 = ops.dropout(d_up1d, drop_cfg[0], drop_cfg[2], drop_cfg[4])

@@ -75,7 +75,7 @@ def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, o
     c1 = cins[1] if len(cins) > 1 else 0
     call("icl_conv3d_umma_fwd", P(pks[0]), c_int(cins[0]), P(pk1), c_int(c1), P(wp), P(bias), P(y0), c_int(y0.shape[-1]), P(y1),
          c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), c_int(planes()), c_int(_MAX_CTAS),
-         gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W)
+         gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W, tag="B%d r%d %s->%d" % (B, D, "+".join(map(str, cins)), cout))
     return y0 if split is None else (y0, y1)
 
 
@@ -113,7 +113,7 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     off = 0
     for i, (x, c) in enumerate(zip(xs, cins)):
         call("icl_conv3d_wgrad", P(x), c_int(c), P(dy), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(db if i == 0 else None),
-             c_int(B), c_int(D), c_int(H), c_int(W), gflop=2e-9 * 27 * c * cout * B * D * H * W)
+             c_int(B), c_int(D), c_int(H), c_int(W), gflop=2e-9 * 27 * c * cout * B * D * H * W, tag="B%d r%d %d->%d" % (B, D, c, cout))
         off += c
     return dw, db
 
@@ -196,7 +196,8 @@ def dropout(x, p, mask=None, seed=0):
 def sgemm(M, N, K, A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias=None, bias_mode=0, act=0, accumulate=False, pre=None, batch=1, sA=0, sB=0,
           sC=0):
     call("icl_sgemm", c_int(M), c_int(N), c_int(K), P(A), c_ll(sam), c_ll(sak), c_ll(sA), P(Bm), c_ll(sbk), c_ll(sbn), c_ll(sB), P(C),
-         c_ll(scm), c_ll(scn), c_ll(sC), c_int(batch), P(bias), c_int(bias_mode), c_int(act), c_int(1 if accumulate else 0), P(pre))
+         c_ll(scm), c_ll(scn), c_ll(sC), c_int(batch), P(bias), c_int(bias_mode), c_int(act), c_int(1 if accumulate else 0), P(pre),
+         gflop=2e-9 * M * N * K * batch, tag="%dx%dx%d b%d" % (M, N, K, batch))
 
 
 def linear_fwd(x2d, w, b, act=0, want_pre=False):
@@ -238,7 +239,7 @@ def linear_wgrad(dy2d, x2d, want_bias=True):
     else:
         sgemm(N, K, M, dy2d, 1, N, x2d, K, 1, dW, K, 1)
         if want_bias:
-            call("icl_colsum", P(dy2d), P(db), c_ll(M), c_int(N), c_int(0))
+            call("icl_colsum", P(dy2d), P(db), c_ll(M), c_int(N), c_int(0), tag="%dx%d" % (M, N))
     return dW, db
 
 
