@@ -12,7 +12,7 @@
 // (SURVEY.md §7.3(2)); "fast" mode (P=1) uses the hi plane only.
 //
 // Shared-memory operand layout = UMMA canonical K-major, no swizzle ("interleave"):
-//   A stage  [plane p][k8 chunk j(2)][halo line (18)][halo w (10)][8 ch]   (written by ONE 5-D TMA box per
+//   A stage  [plane p][k8 chunk j(2)][halo line (18)][halo w (10)][8 ch]   (written by ONE 4-D TMA box per
 //            plane from the PK activation tensor [P][B][C/8][D][H][W][8]); core matrix = 8 consecutive w of
 //            one line (8 x 16 B contiguous), SBO = one halo line (160 B), LBO = one k8 chunk (2880 B).
 //            An in-plane tap (kh,kw) is just a start-address offset of (kh*10 + kw)*16 B, so the 9 taps
@@ -83,10 +83,10 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
   }
 }
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
 }
 __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -185,7 +185,7 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             const int C8 = (src0 ? p.C0 : p.C1) / 8;
             const int ch8 = (src0 ? k0 : k0 - p.C0) / 8;
             for (int pl = 0; pl < P; ++pl)
-              tma_load_5d(sa + pl * UM_A_PLANE_BYTES, map, fb, 0, tc.w0 - 1, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
+              tma_load_4d(sa + pl * UM_A_PLANE_BYTES, map, fb, (tc.w0 - 1) * 8, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
             const __nv_bfloat16* wsrc = p.wp + ((((long long)tc.nt * 3 + kd) * nchunks + c) * (long long)(b_bytes / 2));
             bulk_load(sa + a_bytes, wsrc, b_bytes, fb);
             if (++stage == stages) { stage = 0; phase ^= 1; }
@@ -375,11 +375,13 @@ static EncodeTiledFn get_encode() {
 static int make_pk_map(CUtensorMap* map, const void* pk, int P, int B, int C, int D, int H, int W) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { icl_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }
-  const cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)P * B * (C / 8)};
-  const cuuint64_t strides[4] = {16, (cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
-  const cuuint32_t box[5] = {8, UM_HW, UM_HL, 1, 2};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(pk), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+  // (w, 8 channels) is contiguous in PK, so it is ONE tensor-map dimension of 8*W elements: a halo line is a single
+  // 160-byte box row instead of ten 16-byte ones (TMA cost is per box row); out-of-range w still zero-fills.
+  const cuuint64_t dims[4] = {(cuuint64_t)W * 8, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)P * B * (C / 8)};
+  const cuuint64_t strides[3] = {(cuuint64_t)W * 16, (cuuint64_t)H * W * 16, (cuuint64_t)D * H * W * 16};
+  const cuuint32_t box[4] = {8 * UM_HW, UM_HL, 1, 2};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(pk), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { icl_set_error("cuTensorMapEncodeTiled failed (%d) for PK [%d,%d,%d,%d,%d,%d]", (int)r, P, B, C, D, H, W); return -1; }
   return 0;

@@ -15,13 +15,16 @@
 __global__ void __launch_bounds__(256) sgemm_k(
     int M, int N, int K, const float* __restrict__ A, long long sam, long long sak, long long sA,
     const float* __restrict__ Bm, long long sbk, long long sbn, long long sB, float* __restrict__ C, long long scm, long long scn,
-    long long sC, const float* __restrict__ bias, int bias_mode, int act, int accumulate, float* __restrict__ pre) {
+    long long sC, const float* __restrict__ bias, int bias_mode, int act, int accumulate, float* __restrict__ pre, int ksplit, int k_per) {
   __shared__ __align__(16) float As[GK][GM + 4];
   __shared__ __align__(16) float Bs[GK][GN + 4];
-  A += (long long)blockIdx.z * sA;
-  Bm += (long long)blockIdx.z * sB;
-  C += (long long)blockIdx.z * sC;
-  if (pre) pre += (long long)blockIdx.z * sC;
+  // split-K (ksplit > 1): blockIdx.z = batch * ksplit + slice; slices combine with atomics into a C the host zeroed
+  const int bz = blockIdx.z / ksplit, ks = blockIdx.z % ksplit;
+  A += (long long)bz * sA;
+  Bm += (long long)bz * sB;
+  C += (long long)bz * sC;
+  if (pre) pre += (long long)bz * sC;
+  const int kbeg = ks * k_per, kend = min(K, kbeg + k_per);
   const int m0 = blockIdx.y * GM, n0 = blockIdx.x * GN;
   const int t = threadIdx.x, tx = t % 16, ty = t / 16;
   float acc[4][4];
@@ -30,17 +33,17 @@ __global__ void __launch_bounds__(256) sgemm_k(
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (sak == 1), b_nfast = (sbn == 1);
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int m, k;
       if (a_kfast) { k = t % GK; m = t / GK + 16 * j; } else { m = t % GM; k = t / GM + 4 * j; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < K) ? A[gm * sam + gk * sak] : 0.f;
+      As[k][m] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
       int n, kb;
       if (b_nfast) { n = t % GN; kb = t / GN + 4 * j; } else { kb = t % GK; n = t / GK + 16 * j; }
       const int gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < N && gkb < K) ? Bm[gkb * sbk + gn * sbn] : 0.f;
+      Bs[kb][n] = (gn < N && gkb < kend) ? Bm[gkb * sbk + gn * sbn] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -64,14 +67,24 @@ __global__ void __launch_bounds__(256) sgemm_k(
       const int gn = n0 + tx * 4 + j;
       if (gn >= N) continue;
       float v = acc[i][j];
+      const long long o = gm * scm + gn * scn;
+      if (ksplit > 1) {
+        if (ks == 0) { if (bias_mode == 1) v += bias[gn]; else if (bias_mode == 2) v += bias[gm]; }
+        atomicAdd(C + o, v);
+        continue;
+      }
       if (bias_mode == 1) v += bias[gn];
       else if (bias_mode == 2) v += bias[gm];
-      const long long o = gm * scm + gn * scn;
       if (pre) pre[o] = v;
       if (act == 1) v = gelu_erf(v);
       C[o] = accumulate ? C[o] + v : v;
     }
   }
+}
+
+__global__ void zero_strided_k(float* __restrict__ C, int M, int N, long long scm, long long scn, long long sC) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (long long)M * N) C[(long long)blockIdx.y * sC + (i / N) * scm + (i % N) * scn] = 0.f;
 }
 
 ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, long long sA, const float* Bm, long long sbk,
@@ -80,8 +93,25 @@ ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long l
   ICL_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm: bad sizes M=%d N=%d K=%d batch=%d", M, N, K, batch);
   dim3 grid(cdiv(N, GN), cdiv(M, GM), batch);
   ICL_REQUIRE(grid.y <= 65535, "sgemm: M too large for grid.y");
+  // few output tiles + long reduction (weight gradients of 1x1x1 convs / Linears over all voxels): split K over the SMs
+  const long long tiles = (long long)grid.x * grid.y * batch;
+  int ksplit = 1, k_per = K;
+  if (tiles < 148 && K >= 4096 && act == 0 && pre == nullptr) {
+    ksplit = (int)((148 * 4 + tiles - 1) / tiles);
+    if (ksplit > K / 1024) ksplit = K / 1024;
+    if ((long long)batch * ksplit > 65535) ksplit = 65535 / batch;
+    k_per = cdiv(cdiv(K, ksplit), GK) * GK;
+    ksplit = cdiv(K, k_per);
+  }
+  if (ksplit > 1) {
+    if (!accumulate) {
+      zero_strided_k<<<dim3(cdiv((long long)M * N, 256), batch), 256, 0, as_stream(stream)>>>(C, M, N, scm, scn, sC);
+      icl_count_launch(1);
+    }
+    grid.z = batch * ksplit;
+  }
   sgemm_k<<<grid, 256, 0, as_stream(stream)>>>(M, N, K, A, sam, sak, sA, Bm, sbk, sbn, sB, C, scm, scn, sC, bias, bias_mode, act,
-                                               accumulate, pre);
+                                               accumulate, pre, ksplit, k_per);
   ICL_LAUNCHED("sgemm");
 }
 
@@ -260,23 +290,58 @@ ICL_API int icl_outer_wgrad(int M, int N, int K, const float* dy, const float* x
 }
 
 // column sums: out[n] (+)= sum_m a[m*N + n]   (bias gradients of Linear layers)
-__global__ void colsum_k(const float* __restrict__ a, float* __restrict__ out, long long M, int N, int accumulate) {
+__global__ void colsum_k(const float* __restrict__ a, float* __restrict__ out, long long M, int N, int accumulate, long long m_per) {
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);
   const int r = threadIdx.x >> 5;  // 8 row lanes
   __shared__ float red[8][33];
+  const long long mbeg = (long long)blockIdx.y * m_per, mend = min(M, mbeg + m_per);
   float s = 0.f;
   if (n < N)
-    for (long long m = r; m < M; m += 8) s += a[m * N + n];
+    for (long long m = mbeg + r; m < mend; m += 8) s += a[m * N + n];
   red[r][threadIdx.x & 31] = s;
   __syncthreads();
   if (r == 0 && n < N) {
     float t = 0.f;
     for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x & 31];
-    out[n] = accumulate ? out[n] + t : t;
+    if (gridDim.y > 1) atomicAdd(out + n, t);
+    else out[n] = accumulate ? out[n] + t : t;
+  }
+}
+// narrow matrices (N in {1,2,4,8,16}, e.g. the bias gradient of the K-class 1x1x1 head over all voxels): element i
+// belongs to column i % N; the grid-stride is a multiple of 32, so a thread stays on column (lane % N) and a warp
+// reads contiguous memory.  Lanes of equal column combine by xor-shuffles, warps through shared memory, blocks by atomics.
+__global__ void __launch_bounds__(256) colsum_narrow_k(const float* __restrict__ a, float* __restrict__ out, long long total, int N) {
+  __shared__ float red[8][16];
+  float s = 0.f;
+  const long long stride = (long long)gridDim.x * 256;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += stride) s += a[i];
+  for (int o = 16; o >= N; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (lane < N) red[wid][lane] = s;
+  __syncthreads();
+  if (threadIdx.x < N) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    atomicAdd(out + threadIdx.x, t);
   }
 }
 ICL_API int icl_colsum(const float* a, float* out, long long M, int N, int accumulate, void* stream) {
-  colsum_k<<<cdiv(N, 32), 256, 0, as_stream(stream)>>>(a, out, M, N, accumulate);
+  if (N <= 16 && (32 % N) == 0 && M >= 65536) {
+    if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, as_stream(stream));
+    colsum_narrow_k<<<148 * 4, 256, 0, as_stream(stream)>>>(a, out, M * N, N);
+    ICL_LAUNCHED("colsum_narrow");
+  }
+  int ysplit = 1;
+  long long m_per = M;
+  if (M >= 16384 && cdiv(N, 32) < 148) {
+    ysplit = (148 * 2) / cdiv(N, 32);
+    if (ysplit > M / 2048) ysplit = (int)(M / 2048);
+    if (ysplit < 1) ysplit = 1;
+    m_per = (M + ysplit - 1) / ysplit;
+    ysplit = (int)((M + m_per - 1) / m_per);
+  }
+  if (ysplit > 1 && !accumulate) cudaMemsetAsync(out, 0, sizeof(float) * N, as_stream(stream));
+  colsum_k<<<dim3(cdiv(N, 32), ysplit), 256, 0, as_stream(stream)>>>(a, out, M, N, accumulate, m_per);
   ICL_LAUNCHED("colsum");
 }
 

@@ -229,6 +229,23 @@ def test_linear_fwd_bwd(M, N, K):
         assert_close(bc.grad.cpu(), gb, 2e-5, "linear db")
 
 
+@pytest.mark.parametrize("M,N,K", [(100000, 16, 2), (70001, 64, 64), (33000, 128, 64)])
+def test_linear_long_reduction_splitk(M, N, K):
+    """1x1x1-conv / Linear weight and bias gradients reduce over all voxels: split-K sgemm + parallel column sums
+    (the reference shapes are final: rows = B*96^3, proj/fc_kv: rows = B*24^3)."""
+    import icl_b200.functional as Fn
+    x = torch.randn(M, K, generator=g(1), requires_grad=True)
+    w = (torch.randn(N, K, generator=g(2)) / K ** 0.5).requires_grad_(True)
+    b = torch.randn(N, generator=g(3)).requires_grad_(True)
+    dy = torch.randn(M, N, generator=g(4))
+    gx, gw, gb = torch.autograd.grad(F.linear(x.double(), w.double(), b.double()), (x, w, b), dy.double())
+    xc, wc, bc = (t.detach().cuda().requires_grad_(True) for t in (x, w, b))
+    Fn.linear(xc, wc, bc, 0).backward(dy.cuda())
+    assert_close(xc.grad.cpu(), gx, 2e-5, "dx")
+    assert_close(wc.grad.cpu(), gw, 2e-5, "dw split-K")
+    assert_close(bc.grad.cpu(), gb, 2e-5, "db split rows")
+
+
 @pytest.mark.parametrize("rows,C", [(10, 64), (6, 1728), (33, 100)])
 def test_layernorm(rows, C):
     import icl_b200.functional as Fn
