@@ -20,8 +20,7 @@
 //   B stage  [plane p][tap 9][k8 chunk 2][n NT][8 ch]  (one 1-D bulk copy; weights pre-packed per stage),
 //            core matrix = 8 n x 16 B, SBO = 128 B, LBO = NT*16 B.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
-#include "common.cuh"
-#include <cuda.h>
+#include "umma.cuh"
 
 #define UM_TH 16
 #define UM_TW 8
@@ -49,75 +48,6 @@ struct UmmaConvParams {
   int stages, P;
   int tmem_cols;
 };
-
-// ------------------------------------------------------------------------------------------
-// PTX wrappers
-// ------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (kernel error) instead of hanging the GPU box.
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("icl conv3d_umma: mbarrier wait timeout (tag %d, block %d, thread %d)\n", tag, blockIdx.x, threadIdx.x);
-      __trap();
-    }
-  }
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-// smem matrix descriptor, SWIZZLE_NONE, version 1 (sm_100): start>>4 | LBO>>4 <<16 | SBO>>4 <<32 | 1<<46
-__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46);
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct TileCoord { int nt, b, d, h0, w0; };
 __device__ __forceinline__ TileCoord decode_tile(long long t, const UmmaConvParams& p) {
@@ -275,12 +205,27 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
         if (p.stats) {
+          // column sums over the warp's 32 rows by a transposing butterfly: every exchange halves the number of
+          // columns a lane still carries (16 -> 8 -> 4 -> 2 -> 1), 16 shuffles per statistic instead of 80; lane l
+          // ends with column (l >> 1): even lanes hold its sum, odd lanes its sum of squares.
+          float a[16], q[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float x = valid ? v[i] : 0.f;
-            const float s = warp_sum(x), s2 = warp_sum(x * x);
-            if (lane == 0) { atomicAdd(&sstat[n + i][0], s); atomicAdd(&sstat[n + i][1], s2); }
+          for (int i = 0; i < 16; ++i) { a[i] = valid ? v[i] : 0.f; q[i] = a[i] * a[i]; }
+#pragma unroll
+          for (int o = 16; o >= 2; o >>= 1) {
+            const int half = o >> 1;
+            const bool upper = (lane & o) != 0;
+#pragma unroll
+            for (int j = 0; j < half; ++j) {
+              const float sa = upper ? a[j] : a[j + half], sq = upper ? q[j] : q[j + half];
+              const float ka = upper ? a[j + half] : a[j], kq = upper ? q[j + half] : q[j];
+              a[j] = ka + __shfl_xor_sync(0xffffffffu, sa, o);
+              q[j] = kq + __shfl_xor_sync(0xffffffffu, sq, o);
+            }
           }
+          const float ta = a[0] + __shfl_xor_sync(0xffffffffu, a[0], 1);
+          const float tq = q[0] + __shfl_xor_sync(0xffffffffu, q[0], 1);
+          atomicAdd(&sstat[n + (lane >> 1)][lane & 1], (lane & 1) ? tq : ta);
         }
       }
       tc_fence_before();
@@ -359,19 +304,6 @@ ICL_API int icl_umma_ntile(int N) {
 // ------------------------------------------------------------------------------------------
 // host side: tensor maps + launch
 // ------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess && qres == cudaDriverEntryPointSuccess)
-      fn = (EncodeTiledFn)ptr;
-  }
-  return fn;
-}
 static int make_pk_map(CUtensorMap* map, const void* pk, int P, int B, int C, int D, int H, int W) {
   EncodeTiledFn enc = get_encode();
   if (!enc) { icl_set_error("cuTensorMapEncodeTiled entry point unavailable"); return -1; }

@@ -174,7 +174,9 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
 
 __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
                                           const double* __restrict__ red, float* __restrict__ dY, __nv_bfloat16* __restrict__ pk,
-                                          int write_lo, int B, int C, long long S) {
+                                          int write_lo, int B, int C, long long S, float* __restrict__ dbias) {
+  __shared__ float bsum[8][8];
+  float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int C8 = C >> 3;
   const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
   float mean[8], rstd[8], mg[8], mgy[8];
@@ -198,9 +200,24 @@ __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const fl
       const float yh = (yv[i] - mean[i]) * rstd[i];
       const float g = yh > 0.f ? gv[i] : 0.f;
       o[i] = rstd[i] * (g - mg[i] - yh * mgy[i]);
+      bacc[i] += o[i];
     }
     if (dY) st8(dY + off, o);
     if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, o);
+  }
+  if (dbias) {  // conv-bias gradient = sum over voxels (and samples) of dY: warp -> block -> one atomic per channel
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float t = warp_sum(bacc[i]);
+      if (lane == 0) bsum[wid][i] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += bsum[w][threadIdx.x];
+      atomicAdd(dbias + c8 * 8 + threadIdx.x, t);
+    }
   }
 }
 __global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
@@ -216,7 +233,7 @@ __global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, 
   }
 }
 ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red /* [B,C,2] zeroed */, float* dY,
-                                  void* pk, int write_lo, int B, int C, long long S, void* stream) {
+                                  void* pk, int write_lo, float* dbias /* [C] zeroed, or null */, int B, int C, long long S, void* stream) {
   ICL_REQUIRE(C <= 1024, "instnorm_relu_bwd: C=%d > 1024", C);
   int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 65535) / 65536);
   if (chunks < 1) chunks = 1;
@@ -224,9 +241,9 @@ ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* 
   icl_count_launch(1);
   if (C % 8 == 0) {
     int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
-    instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S);
+    instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S, dbias);
   } else {
-    ICL_REQUIRE(pk == nullptr && dY != nullptr, "instnorm_relu_bwd: PK output needs C %% 8 == 0 (C=%d)", C);
+    ICL_REQUIRE(pk == nullptr && dY != nullptr && dbias == nullptr, "instnorm_relu_bwd: PK / bias-gradient outputs need C %% 8 == 0 (C=%d)", C);
     long long total = (long long)B * S * C;
     instnorm_relu_bwd_apply_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, C, S, total);
   }

@@ -65,8 +65,13 @@ def _half_bwd(h, dA, need_dx):
     cout = h.w.shape[0]
     B, D, H, W, _ = h.y.shape
     dgrad_umma = need_dx and ops.umma_ok([cout], sum(cins)) and all(c % 16 == 0 for c in cins)
-    dY, dY_pk = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma)
-    dw, db = ops.conv3d_wgrad([s.f32 for s in h.srcs], cins, dY, cout, B, D, H, W)
+    wgrad_umma = ops.wgrad_umma_ok(cins, cout) and all(s.pk is not None for s in h.srcs)
+    if wgrad_umma:
+        dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True)
+        dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W)
+    else:
+        dY, dY_pk = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma)
+        dw, db = ops.conv3d_wgrad([s.f32 for s in h.srcs], cins, dY, cout, B, D, H, W)
     if not need_dx:
         return dw, db, None
     cin_total = sum(cins)

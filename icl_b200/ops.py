@@ -118,6 +118,30 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     return dw, db
 
 
+def wgrad_umma_ok(cins, cout):
+    if os.environ.get("ICL_DISABLE_UMMA") == "1":
+        return False
+    return all(c % 16 == 0 for c in cins) and cout % 16 == 0
+
+
+def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W):
+    """Tensor-core weight gradient from PK operands.  Returns dw [Cout, sum(cins), 3,3,3] (no bias gradient)."""
+    cin_total = sum(cins)
+    dev = dy_pk.device
+    dw = torch.empty((cout, cin_total, 3, 3, 3), dtype=torch.float32, device=dev)
+    off = 0
+    for pk, c in zip(x_pks, cins):
+        slots = _lib.lib().icl_conv3d_wgrad_umma_slots(c, cout, B, D, H, W)
+        if slots <= 0:
+            raise RuntimeError("conv3d_wgrad_umma: unsupported shape Cin=%d Cout=%d D=%d" % (c, cout, D))
+        ws = torch.empty(slots * 9 * 64 * 32, dtype=torch.float32, device=dev)
+        call("icl_conv3d_wgrad_umma", P(pk), c_int(c), P(dy_pk), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(ws), c_int(B),
+             c_int(D), c_int(H), c_int(W), c_int(planes()), c_int(0), gflop=2e-9 * 27 * c * cout * B * D * H * W,
+             tag="B%d r%d %d->%d" % (B, D, c, cout))
+        off += c
+    return dw
+
+
 # ------------------------------------------------------------------------------------------
 # InstanceNorm + ReLU, pool, upsample, dropout
 # ------------------------------------------------------------------------------------------
@@ -137,14 +161,16 @@ def instnorm_relu_fwd(y, mr, want_pk):
     return a, pk
 
 
-def instnorm_relu_bwd(dA, y, mr, want_pk):
+def instnorm_relu_bwd(dA, y, mr, want_pk, want_dbias=False):
+    """Returns (dY, dY_pk or None[, dbias]) — dbias = sum of dY over samples and voxels (the conv-bias gradient)."""
     B, D, H, W, C = y.shape
     red = torch.zeros((B, C, 2), dtype=torch.float64, device=y.device)
     dY = torch.empty_like(y)
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
-    call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C),
+    db = torch.zeros((C,), dtype=torch.float32, device=y.device) if want_dbias else None
+    call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), P(db), c_int(B), c_int(C),
          c_ll(D * H * W), mbytes=1e-6 * y.numel() * (20 + (2 * planes() if want_pk else 0)))
-    return dY, pk
+    return (dY, pk, db) if want_dbias else (dY, pk)
 
 
 def pack_pk(x):

@@ -38,6 +38,11 @@ int icl_umma_ntile(int N);
 int icl_conv3d_direct_fwd(const float* x0, int C0, const float* x1, int C1, const float* wp, const float* bias, float* y, int ldy,
                           int y_coff, double* stats, int B, int D, int H, int W, int Cout, void* stream);
 int icl_repack_w_f32(const float* w, float* wp, int Cout, int Cin, int dgrad, void* stream);
+/* tcgen05 weight gradient: reduction over voxels, PK operands used in place as MN-major UMMA tiles; `workspace` holds
+   icl_conv3d_wgrad_umma_slots() * 9*64*32 floats of per-CTA partial sums, reduced in a fixed order into dw. */
+int icl_conv3d_wgrad_umma_slots(int Cin, int Cout, int B, int D, int H, int W);
+int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, int Cout, float* dw, int Cin_total, int ci_off, float* workspace, int B,
+                          int D, int H, int W, int P, int accumulate, void* stream);
 int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, float* dw, int Cin_total, int ci_off, float* dbias, int B, int D,
                      int H, int W, void* stream);
 
@@ -45,8 +50,8 @@ int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, float* d
 int icl_instnorm_stats(const float* y, double* stats, int B, int C, long long S, void* stream);
 int icl_instnorm_finalize(const double* stats, float* mr, int B, int C, long long S, float eps, void* stream);
 int icl_instnorm_relu_fwd(const float* y, const float* mr, float* a, void* pk, int write_lo, int B, int C, long long S, void* stream);
-int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red, float* dY, void* pk, int write_lo, int B, int C,
-                          long long S, void* stream);
+int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red, float* dY, void* pk, int write_lo, float* dbias,
+                          int B, int C, long long S, void* stream);
 int icl_pack_pk(const float* x, void* pk, int write_lo, int B, int C, long long S, void* stream);
 
 /* ---- nn.MaxPool3d(2): networks/unet_3D_icl.py:41,45,49,53 (first max in scan order wins ties) ---- */

@@ -129,6 +129,37 @@ def test_conv3d_umma_persistent_loop_and_dgrad_split():
     assert_close(uncl(d1), x.grad[:, 16:], 2e-4, "dgrad up part")
 
 
+WGRAD_CASES = [
+    # B, cins, cout, (D,H,W)
+    (1, [16], 16, (2, 16, 8)),       # one window step, one tile
+    (2, [16], 16, (6, 32, 24)),      # several steps / tiles / samples -> several splits
+    (1, [32], 16, (4, 24, 12)),      # ragged tiles, two ci tiles
+    (1, [16, 32], 16, (4, 16, 16)),  # virtual concat (up1 shape): two sources
+    (1, [64], 64, (4, 12, 12)),
+    (1, [128], 256, (2, 6, 6)),      # more output blocks than SMs
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("parity", 2e-4), ("fast", 3e-2)])
+@pytest.mark.parametrize("B,cins,cout,dims", WGRAD_CASES)
+def test_conv3d_wgrad_umma(B, cins, cout, dims, mode, tol):
+    import icl_b200
+    ops = _ops()
+    icl_b200.set_precision(mode)
+    try:
+        D, H, W = dims
+        xs = [torch.randn(B, c, D, H, W, generator=g(i)) for i, c in enumerate(cins)]
+        dy = torch.randn(B, cout, D, H, W, generator=g(4))
+        xcat = torch.cat(xs, 1).double().requires_grad_(True)
+        w = torch.zeros(cout, sum(cins), 3, 3, 3, dtype=torch.float64, requires_grad=True)
+        F.conv3d(xcat, w, None, padding=1).backward(dy.double())
+        dw = ops.conv3d_wgrad_umma([ops.pack_pk(cl(x)) for x in xs], cins, ops.pack_pk(cl(dy)), cout, B, D, H, W)
+        torch.cuda.synchronize()
+        assert_close(dw.cpu(), w.grad, tol, "wgrad umma %s" % mode)
+    finally:
+        icl_b200.set_precision("parity")
+
+
 # ------------------------------------------------------------------------------------------ norm / pool / upsample / dropout
 @pytest.mark.parametrize("C", [16, 5])
 def test_instnorm_relu_fwd_bwd(C):
@@ -147,7 +178,12 @@ def test_instnorm_relu_fwd_bwd(C):
     if pk is not None:
         rec = (pk[0].float() + pk[1].float()).permute(0, 1, 5, 2, 3, 4).reshape(B, C, D, H, W).cpu()
         assert_close(rec, a_ref.detach(), 2e-5, "PK hi+lo")
-    dY, dpk = ops.instnorm_relu_bwd(cl(dA), yc, mr, C % 16 == 0)
+    if C % 8 == 0:
+        dY, dpk, db = ops.instnorm_relu_bwd(cl(dA), yc, mr, C % 16 == 0, want_dbias=True)
+        # the bias gradient in front of InstanceNorm is mathematically zero: compare with an absolute floor
+        assert_close(db.cpu(), y.grad.sum((0, 2, 3, 4)), 1e-3, "dbias", abs_floor=1e-4)
+    else:
+        dY, dpk = ops.instnorm_relu_bwd(cl(dA), yc, mr, False)
     assert_close(uncl(dY), y.grad, 2e-5, "IN+ReLU bwd")
     if dpk is not None:
         rec = (dpk[0].float() + dpk[1].float()).permute(0, 1, 5, 2, 3, 4).reshape(B, C, D, H, W).cpu()
