@@ -21,6 +21,7 @@
 //            core matrix = 8 n x 16 B, SBO = 128 B, LBO = NT*16 B.
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM alloc + MMA issuer, warps 2-5 = epilogue.
 #include "umma.cuh"
+#include <stdlib.h>
 
 #define UM_TH 16
 #define UM_TW 8
@@ -47,16 +48,19 @@ struct UmmaConvParams {
   long long num_tiles;
   int stages, P;
   int tmem_cols;
+  int dbg;
 };
 
 struct TileCoord { int nt, b, d, h0, w0; };
-__device__ __forceinline__ TileCoord decode_tile(long long t, const UmmaConvParams& p) {
+// 32-bit arithmetic only: a 64-bit division costs ~100 dependent instructions and this runs once per tile in each of
+// the three single-thread roles (the host checks num_tiles < 2^31).
+__device__ __forceinline__ TileCoord decode_tile(int t, const UmmaConvParams& p) {
   TileCoord c;
-  c.nt = (int)(t % p.n_tiles); t /= p.n_tiles;
-  c.w0 = (int)(t % p.tiles_w) * UM_TW; t /= p.tiles_w;
-  c.h0 = (int)(t % p.tiles_h) * UM_TH; t /= p.tiles_h;
-  c.d = (int)(t % p.D);
-  c.b = (int)(t / p.D);
+  c.nt = t % p.n_tiles; t /= p.n_tiles;
+  c.w0 = (t % p.tiles_w) * UM_TW; t /= p.tiles_w;
+  c.h0 = (t % p.tiles_h) * UM_TH; t /= p.tiles_h;
+  c.d = t % p.D;
+  c.b = t / p.D;
   return c;
 }
 
@@ -99,7 +103,7 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     // ================================ TMA producer ================================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(t, p);
         for (int kd = 0; kd < 3; ++kd) {
           const int dz = tc.d + kd - 1;
@@ -108,13 +112,13 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
             const uint32_t sa = smem0 + stage * stage_bytes;
             const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, stage_bytes);
+            mbar_expect_tx(fb, (p.dbg & 8) ? b_bytes : stage_bytes);
             const int k0 = c * UM_KC;
             const bool src0 = k0 < p.C0;
             const CUtensorMap* map = src0 ? &mapA0 : &mapA1;
             const int C8 = (src0 ? p.C0 : p.C1) / 8;
             const int ch8 = (src0 ? k0 : k0 - p.C0) / 8;
-            for (int pl = 0; pl < P; ++pl)
+            for (int pl = 0; pl < P && !(p.dbg & 8); ++pl)
               tma_load_4d(sa + pl * UM_A_PLANE_BYTES, map, fb, (tc.w0 - 1) * 8, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
             const __nv_bfloat16* wsrc = p.wp + ((((long long)tc.nt * 3 + kd) * nchunks + c) * (long long)(b_bytes / 2));
             bulk_load(sa + a_bytes, wsrc, b_bytes, fb);
@@ -129,7 +133,7 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
         const TileCoord tc = decode_tile(t, p);
         mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, 200 + acc);
         tc_fence_after();
@@ -144,13 +148,14 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
             const uint32_t sa = smem0 + stage * stage_bytes;
             const uint32_t sb = sa + a_bytes;
 #pragma unroll
-            for (int t9 = 0; t9 < 9; ++t9) {
-              const uint32_t aoff = (uint32_t)(((t9 / 3) * UM_HW + (t9 % 3)) * 16);
+            for (int t9 = 0; t9 < ((p.dbg & 4) ? 1 : 9); ++t9) {
+              const uint32_t aoff = (p.dbg & 64) ? 0u : (uint32_t)(((t9 / 3) * UM_HW + (t9 % 3)) * 16);
               const uint64_t a_hi = umma_desc(sa + aoff, UM_A_LBO, UM_A_SBO);
               const uint64_t b_hi = umma_desc(sb + t9 * (NT * 32), NT * 16, 128);
-              umma_bf16(tmem_d, a_hi, b_hi, idesc, accumulate);
+              const uint32_t tmem_dd = (p.dbg & 32) ? (tmem_base + (uint32_t)((t9 & 1) * NT)) : tmem_d;
+              umma_bf16(tmem_dd, a_hi, b_hi, idesc, accumulate);
               accumulate = 1;
-              if (P == 2) {
+              if (P == 2 && !(p.dbg & 16)) {
                 const uint64_t a_lo = umma_desc(sa + UM_A_PLANE_BYTES + aoff, UM_A_LBO, UM_A_SBO);
                 const uint64_t b_lo = umma_desc(sb + b_plane + t9 * (NT * 32), NT * 16, 128);
                 umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
@@ -173,7 +178,7 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     const int et = threadIdx.x - 64;      // 0..127
     int acc = 0; uint32_t acc_phase = 0;
     int cur_b = -1;
-    for (long long t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+    for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
       const TileCoord tc = decode_tile(t, p);
       if (p.stats && tc.b != cur_b) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -199,12 +204,12 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? p.bias[n + i] : 0.f);
-        if (valid) {
+        if (valid && !(p.dbg & 2)) {
           float* dst = (n < p.split) ? p.y0 + vox * p.ld0 + n : p.y1 + vox * p.ld1 + (n - p.split);
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
-        if (p.stats) {
+        if (p.stats && !(p.dbg & 1)) {
           // column sums over the warp's 32 rows by a transposing butterfly: every exchange halves the number of
           // columns a lane still carries (16 -> 8 -> 4 -> 2 -> 1), 16 shuffles per statistic instead of 80; lane l
           // ends with column (l >> 1): even lanes hold its sum, odd lanes its sum of squares.
@@ -335,8 +340,10 @@ ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1
   ICL_REQUIRE(p.NT >= 16 && Cout % p.NT == 0, "conv3d_umma: no N tile for Cout=%d", Cout);
   ICL_REQUIRE(y1 == nullptr || split % 16 == 0, "conv3d_umma: bad split");
   p.n_tiles = Cout / p.NT;
+  { const char* e = getenv("ICL_UMMA_DBG"); p.dbg = e ? atoi(e) : 0; }
   p.tiles_h = cdiv(H, UM_TH); p.tiles_w = cdiv(W, UM_TW);
   p.num_tiles = (long long)B * D * p.tiles_h * p.tiles_w * p.n_tiles;
+  ICL_REQUIRE(p.num_tiles < (1LL << 31), "conv3d_umma: too many tiles");
   const size_t stage_bytes = (size_t)P * (UM_A_PLANE_BYTES + 9 * p.NT * 32);
   int stages = (int)((200 * 1024) / stage_bytes);
   if (stages > UM_MAX_STAGES) stages = UM_MAX_STAGES;
