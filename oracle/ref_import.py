@@ -62,5 +62,9 @@ def load_test_single_case():
     sys.modules["medpy"].metric = sys.modules["medpy.metric"]
     sys.modules["skimage.measure"].label = None
     sys.modules["networks.net_factory_3d"].net_factory_3d = None
-    mod = importlib.import_module("test_3D_BraTS")
+    argv, sys.argv = sys.argv, sys.argv[:1]  # the script parses argv at import (test_3D_BraTS.py:21-33)
+    try:
+        mod = importlib.import_module("test_3D_BraTS")
+    finally:
+        sys.argv = argv
     return mod.test_single_case
