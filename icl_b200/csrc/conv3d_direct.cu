@@ -237,3 +237,174 @@ ICL_API int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, 
   conv3d_wgrad_k<<<dim3(gx, gy), 128, 0, as_stream(stream)>>>(x, Cx, dy, Cout, dw, Cin_total, ci_off, dbias, B, D, H, W, (int)tiles);
   ICL_LAUNCHED("conv3d_wgrad");
 }
+
+// ------------------------------------------------------------------------------------------
+// Stem: Cin = 1 -> Cout = 16 (conv1.conv1 of the backbone at full resolution, networks/utils.py:104 with
+// in_size = in_channels = 1).  Bandwidth-bound (4 B in, 64 B out per voxel): the generic kernels above would
+// spend 8x the FMAs on zero-padded channels.  Thread = 4 consecutive w voxels x 16 output channels.
+// ------------------------------------------------------------------------------------------
+#define ST_D 4
+#define ST_H 8
+#define ST_W 32
+#define ST_CO 16
+#define ST_HW (ST_W + 2)
+#define ST_HALO ((ST_D + 2) * (ST_H + 2) * ST_HW)
+
+__global__ void __launch_bounds__(256) conv3d_stem_fwd_k(const float* __restrict__ x, const float* __restrict__ w /* [16][1][27] */,
+                                                         const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats,
+                                                         int B, int D, int H, int W) {
+  __shared__ float xs[ST_HALO];
+  __shared__ __align__(16) float ws[27][ST_CO];
+  __shared__ float red[8][2 * ST_CO];
+  const int tw = cdiv(W, ST_W), th = cdiv(H, ST_H), td = cdiv(D, ST_D);
+  int t = blockIdx.x;
+  const int bw = t % tw; t /= tw;
+  const int bh = t % th; t /= th;
+  const int bd = t % td;
+  const int b = t / td;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < 27 * ST_CO; i += 256) ws[i % 27][i / 27] = w[i];  // w[co*27 + tap]
+  for (int i = tid; i < ST_HALO; i += 256) {
+    const int pw = i % ST_HW, ph = (i / ST_HW) % (ST_H + 2), pd = i / (ST_HW * (ST_H + 2));
+    const int gd = bd * ST_D + pd - 1, gh = bh * ST_H + ph - 1, gw = bw * ST_W + pw - 1;
+    xs[i] = (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) ? x[(((long long)b * D + gd) * H + gh) * W + gw] : 0.f;
+  }
+  __syncthreads();
+  const int lw = (tid % 8) * 4, lh = (tid / 8) % ST_H, ld = tid / (8 * ST_H);
+  float acc[4][ST_CO];
+#pragma unroll
+  for (int v = 0; v < 4; ++v)
+#pragma unroll
+    for (int c = 0; c < ST_CO; ++c) acc[v][c] = 0.f;
+#pragma unroll
+  for (int k9 = 0; k9 < 9; ++k9) {
+    const float* row = &xs[((ld + k9 / 3) * (ST_H + 2) + lh + k9 % 3) * ST_HW + lw];
+    float xv[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) xv[i] = row[i];
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const float4* wv = reinterpret_cast<const float4*>(&ws[k9 * 3 + kw][0]);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = wv[q];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          acc[v][q * 4 + 0] = fmaf(xv[v + kw], w4.x, acc[v][q * 4 + 0]);
+          acc[v][q * 4 + 1] = fmaf(xv[v + kw], w4.y, acc[v][q * 4 + 1]);
+          acc[v][q * 4 + 2] = fmaf(xv[v + kw], w4.z, acc[v][q * 4 + 2]);
+          acc[v][q * 4 + 3] = fmaf(xv[v + kw], w4.w, acc[v][q * 4 + 3]);
+        }
+      }
+    }
+  }
+  const int d = bd * ST_D + ld, h = bh * ST_H + lh, w0 = bw * ST_W + lw;
+  float s[ST_CO], q2[ST_CO];
+#pragma unroll
+  for (int c = 0; c < ST_CO; ++c) { s[c] = 0.f; q2[c] = 0.f; }
+  const bool rowok = d < D && h < H;
+#pragma unroll
+  for (int v = 0; v < 4; ++v) {
+    if (rowok && w0 + v < W) {
+      float* dst = y + ((((long long)b * D + d) * H + h) * W + w0 + v) * ST_CO;
+#pragma unroll
+      for (int c = 0; c < ST_CO; ++c) {
+        acc[v][c] += bias ? bias[c] : 0.f;
+        s[c] += acc[v][c]; q2[c] += acc[v][c] * acc[v][c];
+      }
+#pragma unroll
+      for (int c = 0; c < ST_CO; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(acc[v][c], acc[v][c + 1], acc[v][c + 2], acc[v][c + 3]);
+    }
+  }
+  if (stats) {
+    const int lane = tid & 31, wid = tid >> 5;
+#pragma unroll
+    for (int c = 0; c < ST_CO; ++c) {
+      const float a = warp_sum(s[c]), bq = warp_sum(q2[c]);
+      if (lane == 0) { red[wid][c] = a; red[wid][ST_CO + c] = bq; }
+    }
+    __syncthreads();
+    if (tid < 2 * ST_CO) {
+      double tsum = 0.0;
+      for (int k = 0; k < 8; ++k) tsum += (double)red[k][tid];
+      atomicAdd(&stats[((long long)b * ST_CO + (tid % ST_CO)) * 2 + (tid >= ST_CO ? 1 : 0)], tsum);
+    }
+  }
+}
+ICL_API int icl_conv3d_stem_fwd(const float* x, const float* w, const float* bias, float* y, double* stats, int B, int D, int H, int W, int Cout,
+                                void* stream) {
+  ICL_REQUIRE(Cout == ST_CO, "conv3d_stem_fwd: Cout=%d (only 16 is built)", Cout);
+  const long long tiles = (long long)B * cdiv(D, ST_D) * cdiv(H, ST_H) * cdiv(W, ST_W);
+  ICL_REQUIRE(tiles < 2147483647LL, "conv3d_stem_fwd: too many tiles");
+  conv3d_stem_fwd_k<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(x, w, bias, y, stats, B, D, H, W);
+  ICL_LAUNCHED("conv3d_stem_fwd");
+}
+
+#define SW_D 2
+#define SW_HALO ((SW_D + 2) * (ST_H + 2) * ST_HW)
+// stem weight gradient: dw[co][0][tap] = sum_v dy[v][co] * x[v + tap - 1].  Thread = (4 co) x (kd,kh) x (3 kw) = 12 accumulators,
+// 36 threads cover the 16 x 27 outputs, 3 such groups split a tile's rows; a 3-wide register window slides along w.
+__global__ void __launch_bounds__(128) conv3d_stem_wgrad_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                           int B, int D, int H, int W, int tiles_total) {
+  __shared__ float xs[SW_HALO];
+  __shared__ __align__(16) float ds[SW_D * ST_H * ST_W][ST_CO];
+  const int tid = threadIdx.x;
+  const int co4 = tid % 4, k9 = (tid / 4) % 9, part = tid / 36;  // part 3 (threads 108..127) only helps staging
+  const int tw = cdiv(W, ST_W), th = cdiv(H, ST_H), td = cdiv(D, SW_D);
+  float acc[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x) {
+    int t = tile;
+    const int bw = t % tw; t /= tw;
+    const int bh = t % th; t /= th;
+    const int bd = t % td;
+    const int b = t / td;
+    __syncthreads();
+    for (int i = tid; i < SW_HALO; i += 128) {
+      const int pw = i % ST_HW, ph = (i / ST_HW) % (ST_H + 2), pd = i / (ST_HW * (ST_H + 2));
+      const int gd = bd * SW_D + pd - 1, gh = bh * ST_H + ph - 1, gw = bw * ST_W + pw - 1;
+      xs[i] = (gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W) ? x[(((long long)b * D + gd) * H + gh) * W + gw] : 0.f;
+    }
+    for (int i = tid; i < SW_D * ST_H * ST_W * 4; i += 128) {
+      const int q = i % 4, pos = i / 4;
+      const int pw = pos % ST_W, ph = (pos / ST_W) % ST_H, pd = pos / (ST_W * ST_H);
+      const int gd = bd * SW_D + pd, gh = bh * ST_H + ph, gw = bw * ST_W + pw;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (gd < D && gh < H && gw < W) v = *reinterpret_cast<const float4*>(dy + ((((long long)b * D + gd) * H + gh) * W + gw) * ST_CO + q * 4);
+      *reinterpret_cast<float4*>(&ds[pos][q * 4]) = v;
+    }
+    __syncthreads();
+    if (part < 3) {
+      for (int row = part; row < SW_D * ST_H; row += 3) {
+        const int ld = row / ST_H, lh = row % ST_H;
+        const float* xr = &xs[((ld + k9 / 3) * (ST_H + 2) + lh + k9 % 3) * ST_HW];
+        float x0 = xr[0], x1 = xr[1];
+#pragma unroll 4
+        for (int lw = 0; lw < ST_W; ++lw) {
+          const float x2 = xr[lw + 2];
+          const float4 g = *reinterpret_cast<const float4*>(&ds[row * ST_W + lw][co4 * 4]);
+          acc[0][0] = fmaf(x0, g.x, acc[0][0]); acc[0][1] = fmaf(x0, g.y, acc[0][1]); acc[0][2] = fmaf(x0, g.z, acc[0][2]); acc[0][3] = fmaf(x0, g.w, acc[0][3]);
+          acc[1][0] = fmaf(x1, g.x, acc[1][0]); acc[1][1] = fmaf(x1, g.y, acc[1][1]); acc[1][2] = fmaf(x1, g.z, acc[1][2]); acc[1][3] = fmaf(x1, g.w, acc[1][3]);
+          acc[2][0] = fmaf(x2, g.x, acc[2][0]); acc[2][1] = fmaf(x2, g.y, acc[2][1]); acc[2][2] = fmaf(x2, g.z, acc[2][2]); acc[2][3] = fmaf(x2, g.w, acc[2][3]);
+          x0 = x1; x1 = x2;
+        }
+      }
+    }
+  }
+  if (part < 3) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(dw + (co4 * 4 + c) * 27 + k9 * 3 + kw, acc[kw][c]);
+  }
+}
+ICL_API int icl_conv3d_stem_wgrad(const float* x, const float* dy, float* dw /* zeroed [16][1][27] */, int B, int D, int H, int W, int Cout,
+                                  void* stream) {
+  ICL_REQUIRE(Cout == ST_CO, "conv3d_stem_wgrad: Cout=%d (only 16 is built)", Cout);
+  const long long tiles = (long long)B * cdiv(D, SW_D) * cdiv(H, ST_H) * cdiv(W, ST_W);
+  ICL_REQUIRE(tiles < 2147483647LL, "conv3d_stem_wgrad: too many tiles");
+  const int grid = (int)min(tiles, (long long)148 * 4);
+  conv3d_stem_wgrad_k<<<grid, 128, 0, as_stream(stream)>>>(x, dy, dw, B, D, H, W, (int)tiles);
+  ICL_LAUNCHED("conv3d_stem_wgrad");
+}

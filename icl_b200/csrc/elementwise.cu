@@ -297,7 +297,7 @@ __global__ void maxpool_fwd_k(const float* __restrict__ x, float* __restrict__ o
       const float val = x[((((long long)b * D + d) * H + h) * W + w) * C + c];
       if (p == 0 || val > best || val != val) { best = val; bi = p; }
     }
-    out[i] = best;
+    if (out) out[i] = best;
     idx[i] = (unsigned char)bi;
     if (pk) {
       const long long s = ((long long)dd * Ho + ho) * Wo + wo;
@@ -387,8 +387,46 @@ __global__ void upsample2x_fwd_k(const float* __restrict__ x, float* __restrict_
     }
   }
 }
+// C % 8 == 0: thread = one fine voxel x 8 channels (grid.y = sample x channel group); the 8 coarse corners are 32-byte
+// loads, the PK store is 16 B per plane contiguous along w, the optional fp32 store 32 B.
+__global__ void __launch_bounds__(256) upsample2x_fwd_v8_k(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ pk,
+                                                           int write_lo, int B, int C, int d, int h, int w) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w, C8 = C >> 3;
+  const long long S = (long long)D * H * W;
+  const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
+  const long long plane = (long long)B * C8 * S * 8;
+  const float* xb = x + (long long)b * d * h * w * C + c8 * 8;
+  __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
+  for (long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x; s < S; s += (long long)gridDim.x * blockDim.x) {
+    const int X = (int)(s % W), Y = (int)((s / W) % H), Z = (int)(s / ((long long)W * H));
+    int z0, z1, y0, y1, x0, x1; float lz, ly, lx;
+    up2_src(Z, d, z0, z1, lz); up2_src(Y, h, y0, y1, ly); up2_src(X, w, x0, x1, lx);
+    float c[8][8];
+#define LD(i, zz, yy, xx) unpack8(ld8(xb + (((long long)(zz) * h + (yy)) * w + (xx)) * C), c[i])
+    LD(0, z0, y0, x0); LD(1, z0, y0, x1); LD(2, z0, y1, x0); LD(3, z0, y1, x1);
+    LD(4, z1, y0, x0); LD(5, z1, y0, x1); LD(6, z1, y1, x0); LD(7, z1, y1, x1);
+#undef LD
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      // same association order as ATen's upsample_trilinear3d: w-lerp inside h-lerp inside d-lerp
+      const float v00 = (1.f - lx) * c[0][i] + lx * c[1][i], v01 = (1.f - lx) * c[2][i] + lx * c[3][i];
+      const float v10 = (1.f - lx) * c[4][i] + lx * c[5][i], v11 = (1.f - lx) * c[6][i] + lx * c[7][i];
+      r[i] = (1.f - lz) * ((1.f - ly) * v00 + ly * v01) + lz * ((1.f - ly) * v10 + ly * v11);
+    }
+    if (out) st8(out + ((long long)b * S + s) * C + c8 * 8, r);
+    if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, r);
+  }
+}
 ICL_API int icl_upsample2x_fwd(const float* x, float* out, void* pk, int write_lo, int B, int C, int d, int h, int w, void* stream) {
   ICL_REQUIRE(pk == nullptr || C % 8 == 0, "upsample2x: PK output needs C %% 8 == 0");
+  ICL_REQUIRE(pk != nullptr || out != nullptr, "upsample2x: no output requested");
+  if (C % 8 == 0) {
+    const long long S = 8LL * d * h * w;
+    int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
+    upsample2x_fwd_v8_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, B, C, d, h, w);
+    ICL_LAUNCHED("upsample2x_fwd");
+  }
   long long total = (long long)B * C * 8 * d * h * w;
   upsample2x_fwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, B, C, d, h, w);
   ICL_LAUNCHED("upsample2x_fwd");
@@ -434,8 +472,49 @@ __global__ void upsample2x_bwd_k(const float* __restrict__ dout, int Cd, int c_o
     dx[i] = accumulate ? dx[i] + acc : acc;
   }
 }
+// 4 channels per thread (float4): used when C, Cd and c_off are multiples of 4
+__global__ void __launch_bounds__(256) upsample2x_bwd_v4_k(const float* __restrict__ dout, int Cd, int c_off, float* __restrict__ dx,
+                                                           int accumulate, int B, int C, int d, int h, int w) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w, C4 = C >> 2;
+  const long long total = (long long)B * d * h * w * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long long v = i / C4;
+    const int x = (int)(v % w); v /= w;
+    const int y = (int)(v % h); v /= h;
+    const int z = (int)(v % d);
+    const int b = (int)(v / d);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int dz = -1; dz <= 2; ++dz) {
+      const int Z = 2 * z + dz; const float wz = up2_wt(Z, d, z);
+      if (wz == 0.f) continue;
+#pragma unroll
+      for (int dy = -1; dy <= 2; ++dy) {
+        const int Y = 2 * y + dy; const float wy = up2_wt(Y, h, y);
+        if (wy == 0.f) continue;
+#pragma unroll
+        for (int dxx = -1; dxx <= 2; ++dxx) {
+          const int X = 2 * x + dxx; const float wx = up2_wt(X, w, x);
+          if (wx == 0.f) continue;
+          const float wgt = wz * wy * wx;
+          const float4 g = *reinterpret_cast<const float4*>(dout + ((((long long)b * D + Z) * H + Y) * W + X) * Cd + c_off + c);
+          acc.x += wgt * g.x; acc.y += wgt * g.y; acc.z += wgt * g.z; acc.w += wgt * g.w;
+        }
+      }
+    }
+    float4* o = reinterpret_cast<float4*>(dx + (v = 0, ((((long long)b * d + z) * h + y) * w + x) * C + c));
+    if (accumulate) { const float4 p = *o; acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w; }
+    *o = acc;
+  }
+}
 ICL_API int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int B, int C, int d, int h, int w,
                                void* stream) {
+  if (C % 4 == 0 && Cd % 4 == 0 && c_off % 4 == 0) {
+    upsample2x_bwd_v4_k<<<grid_for((long long)B * (C / 4) * d * h * w, 256), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate, B, C,
+                                                                                                        d, h, w);
+    ICL_LAUNCHED("upsample2x_bwd");
+  }
   long long total = (long long)B * C * d * h * w;
   upsample2x_bwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate, B, C, d, h, w);
   ICL_LAUNCHED("upsample2x_bwd");

@@ -29,11 +29,14 @@ def param_names():
 
 
 class _Act:
-    """An activation in both kernel formats (pk is None when C is not a multiple of 16)."""
-    __slots__ = ("f32", "pk", "C")
+    """An activation in the kernel formats: f32 = NDHWC fp32 (None when only tensor-core consumers read it),
+    pk = split-bf16 operand (None when C is not a multiple of 16)."""
+    __slots__ = ("f32", "pk", "C", "shape")
 
-    def __init__(self, f32, pk):
-        self.f32, self.pk, self.C = f32, pk, f32.shape[-1]
+    def __init__(self, f32, pk, shape=None):
+        self.f32, self.pk = f32, pk
+        self.shape = tuple(f32.shape) if f32 is not None else tuple(shape)
+        self.C = self.shape[-1]
 
 
 class _Half:
@@ -44,13 +47,15 @@ def _half_fwd(srcs, w, b):
     """conv3x3x3(+bias) -> InstanceNorm -> ReLU on the virtual concat of `srcs` (list of _Act)."""
     cins = [s.C for s in srcs]
     cout = w.shape[0]
-    B, D, H, W, _ = srcs[0].f32.shape
+    B, D, H, W, _ = srcs[0].shape
     stats = torch.zeros((B, cout, 2), dtype=torch.float64, device=w.device)
     h = _Half()
     h.srcs, h.w = srcs, w
     h.umma = ops.umma_ok(cins, cout) and all(s.pk is not None for s in srcs)
     if h.umma:
         h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma(w, False), b, cout, B, D, H, W, stats)
+    elif ops.stem_ok(cins, cout):
+        h.y = ops.conv3d_stem_fwd(srcs[0].f32, w, b, B, D, H, W, stats)
     else:
         h.y = ops.conv3d_direct([s.f32 for s in srcs], cins, ops.repack_w_f32(w, False), b, cout, B, D, H, W, stats)
     h.mr = ops.instnorm_finalize(stats, B, cout, D * H * W)
@@ -67,8 +72,12 @@ def _half_bwd(h, dA, need_dx):
     dgrad_umma = need_dx and ops.umma_ok([cout], sum(cins)) and all(c % 16 == 0 for c in cins)
     wgrad_umma = ops.wgrad_umma_ok(cins, cout) and all(s.pk is not None for s in h.srcs)
     if wgrad_umma:
-        dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True)
+        # fp32 dY is only read by the CUDA-core data-gradient fallback
+        dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True, want_f32=need_dx and not dgrad_umma)
         dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W)
+    elif ops.stem_ok(cins, cout):
+        dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma, want_dbias=True)
+        dw = ops.conv3d_stem_wgrad(h.srcs[0].f32, dY, B, D, H, W)
     else:
         dY, dY_pk = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma)
         dw, db = ops.conv3d_wgrad([s.f32 for s in h.srcs], cins, dY, cout, B, D, H, W)
@@ -123,6 +132,9 @@ class Backbone3DFn(torch.autograd.Function):
         wf, bf = p[36], p[37]
         x_ = ops.to_ndhwc(x.detach())
         B, D, H, W, Cin = x_.shape
+        # every conv from the second one on runs on the tensor cores when all channel counts are multiples of 16:
+        # pooled / upsampled tensors are then only ever read as PK operands and their fp32 copies are not written
+        lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16)
         if D % 16 or H % 16 or W % 16:
             raise RuntimeError("unet_3D backbone: spatial size must be a multiple of 16, got %s" % ((D, H, W),))
         rec = {}
@@ -131,9 +143,9 @@ class Backbone3DFn(torch.autograd.Function):
         for i, name in enumerate(["conv1", "conv2", "conv3", "conv4"]):
             rec[name] = _block_fwd([enc], blk[name])
             out = rec[name][1].out
-            pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C))
+            pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C), want_f32=not lean)
             rec["pool%d" % (i + 1)] = idx
-            enc = _Act(pooled, ppk)
+            enc = _Act(pooled, ppk, (B, out.shape[1] // 2, out.shape[2] // 2, out.shape[3] // 2, out.C))
         rec["center"] = _block_fwd([enc], blk["center"])
         center = rec["center"][1].out
         if drop_cfg is not None:
@@ -145,8 +157,9 @@ class Backbone3DFn(torch.autograd.Function):
         coarse = center_d
         for name, skip in (("up_concat4.conv", "conv4"), ("up_concat3.conv", "conv3"), ("up_concat2.conv", "conv2"),
                            ("up_concat1.conv", "conv1")):
-            up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C))
-            rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk)], blk[name])
+            up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
+            cs = coarse.shape
+            rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name])
             coarse = rec[name][1].out
         up1 = coarse
         up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32

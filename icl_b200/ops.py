@@ -105,6 +105,24 @@ def conv3d_direct(xs, cins, wp, bias, cout, B, D, H, W, stats=None):
     return y
 
 
+def stem_ok(cins, cout):
+    return list(cins) == [1] and cout == 16
+
+
+def conv3d_stem_fwd(x, w, bias, B, D, H, W, stats=None):
+    y = torch.empty((B, D, H, W, 16), dtype=torch.float32, device=x.device)
+    call("icl_conv3d_stem_fwd", P(x), P(w), P(bias), P(y), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(16),
+         gflop=2e-9 * 27 * 16 * B * D * H * W, mbytes=1e-6 * B * D * H * W * 68)
+    return y
+
+
+def conv3d_stem_wgrad(x, dy, B, D, H, W):
+    dw = torch.zeros((16, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
+    call("icl_conv3d_stem_wgrad", P(x), P(dy), P(dw), c_int(B), c_int(D), c_int(H), c_int(W), c_int(16),
+         gflop=2e-9 * 27 * 16 * B * D * H * W, mbytes=1e-6 * B * D * H * W * 68)
+    return dw
+
+
 def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     """Returns (dw [Cout, sum(cins), 3,3,3], dbias [Cout] or None)."""
     cin_total = sum(cins)
@@ -161,15 +179,15 @@ def instnorm_relu_fwd(y, mr, want_pk):
     return a, pk
 
 
-def instnorm_relu_bwd(dA, y, mr, want_pk, want_dbias=False):
-    """Returns (dY, dY_pk or None[, dbias]) — dbias = sum of dY over samples and voxels (the conv-bias gradient)."""
+def instnorm_relu_bwd(dA, y, mr, want_pk, want_dbias=False, want_f32=True):
+    """Returns (dY or None, dY_pk or None[, dbias]) — dbias = sum of dY over samples and voxels (the conv-bias gradient)."""
     B, D, H, W, C = y.shape
     red = torch.zeros((B, C, 2), dtype=torch.float64, device=y.device)
-    dY = torch.empty_like(y)
+    dY = torch.empty_like(y) if want_f32 else None
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
     db = torch.zeros((C,), dtype=torch.float32, device=y.device) if want_dbias else None
     call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), P(db), c_int(B), c_int(C),
-         c_ll(D * H * W), mbytes=1e-6 * y.numel() * (20 + (2 * planes() if want_pk else 0)))
+         c_ll(D * H * W), mbytes=1e-6 * y.numel() * (16 + (4 if want_f32 else 0) + (2 * planes() if want_pk else 0)))
     return (dY, pk, db) if want_dbias else (dY, pk)
 
 
@@ -180,9 +198,9 @@ def pack_pk(x):
     return pk
 
 
-def maxpool_fwd(a, want_pk):
+def maxpool_fwd(a, want_pk, want_f32=True):
     B, D, H, W, C = a.shape
-    out = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.float32, device=a.device)
+    out = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.float32, device=a.device) if want_f32 else None
     idx = torch.empty((B, D // 2, H // 2, W // 2, C), dtype=torch.uint8, device=a.device)
     pk = empty_pk(B, C, D // 2, H // 2, W // 2, a.device) if want_pk else None
     call("icl_maxpool3d_fwd", P(a), P(out), P(idx), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_int(D), c_int(H), c_int(W))
@@ -194,11 +212,12 @@ def maxpool_bwd(dout, idx, dx, accumulate):
     call("icl_maxpool3d_bwd", P(dout), P(idx), P(dx), c_int(1 if accumulate else 0), c_int(B), c_int(C), c_int(D), c_int(H), c_int(W))
 
 
-def upsample2x_fwd(x, want_pk):
+def upsample2x_fwd(x, want_pk, want_f32=True):
     B, d, h, w, C = x.shape
-    out = torch.empty((B, 2 * d, 2 * h, 2 * w, C), dtype=torch.float32, device=x.device)
+    out = torch.empty((B, 2 * d, 2 * h, 2 * w, C), dtype=torch.float32, device=x.device) if want_f32 else None
     pk = empty_pk(B, C, 2 * d, 2 * h, 2 * w, x.device) if want_pk else None
-    call("icl_upsample2x_fwd", P(x), P(out), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_int(d), c_int(h), c_int(w))
+    call("icl_upsample2x_fwd", P(x), P(out), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_int(d), c_int(h), c_int(w),
+         mbytes=1e-6 * x.numel() * (4 + 8 * ((4 if want_f32 else 0) + (2 * planes() if want_pk else 0))))
     return out, pk
 
 

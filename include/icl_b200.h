@@ -37,6 +37,10 @@ int icl_umma_ntile(int N);
 /* fp32 CUDA-core path for the Cin=1 stem and channel counts that are not multiples of 16. */
 int icl_conv3d_direct_fwd(const float* x0, int C0, const float* x1, int C1, const float* wp, const float* bias, float* y, int ldy,
                           int y_coff, double* stats, int B, int D, int H, int W, int Cout, void* stream);
+/* Cin = 1 stem (conv1.conv1 at full resolution): bandwidth-bound specialisations, torch weight layout [16][1][27] */
+int icl_conv3d_stem_fwd(const float* x, const float* w, const float* bias, float* y, double* stats, int B, int D, int H, int W, int Cout,
+                        void* stream);
+int icl_conv3d_stem_wgrad(const float* x, const float* dy, float* dw, int B, int D, int H, int W, int Cout, void* stream);
 int icl_repack_w_f32(const float* w, float* wp, int Cout, int Cin, int dgrad, void* stream);
 /* tcgen05 weight gradient: reduction over voxels, PK operands used in place as MN-major UMMA tiles; `workspace` holds
    icl_conv3d_wgrad_umma_slots() * 9*64*32 floats of per-CTA partial sums, reduced in a fixed order into dw. */

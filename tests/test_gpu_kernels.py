@@ -62,6 +62,26 @@ def test_conv3d_direct_dgrad_and_wgrad():
     assert_close(db.cpu(), b.grad, 1e-5, "bgrad")
 
 
+@pytest.mark.parametrize("B,dims", [(2, (8, 16, 32)), (1, (6, 12, 40)), (1, (4, 9, 33))])
+def test_conv3d_stem_fwd_and_wgrad(B, dims):
+    """Cin=1 -> 16 stem specialisations vs F.conv3d and its autograd."""
+    ops = _ops()
+    D, H, W = dims
+    x = torch.randn(B, 1, D, H, W, generator=g(1))
+    w = (torch.randn(16, 1, 3, 3, 3, generator=g(2)) * 0.3).requires_grad_(True)
+    b = torch.randn(16, generator=g(3))
+    dy = torch.randn(B, 16, D, H, W, generator=g(4))
+    ref = F.conv3d(x, w, b, padding=1)
+    ref.backward(dy)
+    stats = torch.zeros(B, 16, 2, dtype=torch.float64, device="cuda")
+    y = ops.conv3d_stem_fwd(cl(x), w.detach().cuda(), b.cuda(), B, D, H, W, stats)
+    assert_close(uncl(y), ref.detach(), 1e-5, "stem fwd")
+    assert_close(stats[..., 0].cpu(), ref.detach().double().sum((2, 3, 4)), 1e-5, "sum", abs_floor=1e-3)
+    assert_close(stats[..., 1].cpu(), (ref.detach().double() ** 2).sum((2, 3, 4)), 1e-5, "sumsq")
+    dw = ops.conv3d_stem_wgrad(cl(x), cl(dy), B, D, H, W)
+    assert_close(dw.cpu(), w.grad, 2e-5, "stem wgrad")
+
+
 def test_conv3d_wgrad_two_sources_96():
     ops = _ops()
     B, cins, cout, D, H, W = 1, [16, 32], 16, 8, 24, 40
@@ -209,15 +229,21 @@ def test_maxpool_ties_first_max():
     assert_close(dx2.cpu(), (base + cl(xr.grad)).cpu(), 1e-6, "accumulate")
 
 
-def test_upsample2x_fwd_bwd():
+@pytest.mark.parametrize("C", [16, 6])
+def test_upsample2x_fwd_bwd(C):
     ops = _ops()
-    B, C, d, h, w = 2, 16, 3, 4, 5
+    B, d, h, w = 2, 3, 4, 5
     x = torch.randn(B, C, d, h, w, generator=g(1), requires_grad=True)
     up = F.interpolate(x, scale_factor=(2, 2, 2), mode="trilinear", align_corners=False)
     dout = torch.randn(up.shape, generator=g(2))
     up.backward(dout)
-    out, pk = ops.upsample2x_fwd(cl(x.detach()), True)
+    out, pk = ops.upsample2x_fwd(cl(x.detach()), C % 8 == 0)
     assert_close(uncl(out), up.detach(), 1e-6, "upsample fwd")
+    if pk is not None:
+        none, pk2 = ops.upsample2x_fwd(cl(x.detach()), True, want_f32=False)  # PK-only variant used by the lean backbone
+        assert none is None and torch.equal(pk, pk2)
+        rec = (pk[0].float() + pk[1].float()).permute(0, 1, 5, 2, 3, 4).reshape(B, C, 2 * d, 2 * h, 2 * w).cpu()
+        assert_close(rec, up.detach(), 2e-5, "upsample PK hi+lo")
     dx = torch.empty(B, d, h, w, C, device="cuda")
     ops.upsample2x_bwd(cl(dout), 0, C, dx, False)
     assert_close(uncl(dx), x.grad, 1e-5, "upsample bwd")
