@@ -167,47 +167,28 @@ __device__ __forceinline__ void voxel_dlogits(const float* __restrict__ src, con
   }
 }
 
-// Interpolated sources, gather form: one thread group per COARSE cell walks the (2*scale)^3 loss-grid voxels whose
-// trilinear footprint touches the cell and reduces weight * dlogit in registers -> warp -> block.  No atomics, no
-// pre-zeroed output, deterministic; the per-voxel work is recomputed by the (up to 8) cells sharing a voxel, which is
-// cheap next to the 256-way shared-memory atomic contention of a scatter at scale 8/16.
-template <int KT>
-__global__ void __launch_bounds__(256) class_stats_bwd_gather_k(const float* __restrict__ src, SrcGeom g, int B, int K,
-                                                                const long long* __restrict__ labels, const float* __restrict__ tgt,
-                                                                int is_prob, const float* __restrict__ class_w,
-                                                                const double* __restrict__ sums, const float* __restrict__ g_ce,
-                                                                const float* __restrict__ g_dice, float w_ce, float w_dice,
-                                                                float* __restrict__ dsrc, int G, long long cells) {
-  __shared__ float cA[KT], cB[KT];
-  __shared__ float cCE;
-  __shared__ float red[8][KT];
-  if (threadIdx.x < K) {
-    const int k = threadIdx.x;
-    const double num = 2.0 * sums[1 + 3 * k] + 1e-5, den = sums[2 + 3 * k] + sums[3 + 3 * k] + 1e-5;
-    const double gd = (g_dice ? (double)g_dice[0] : 0.0) * w_dice / K * (class_w ? (double)class_w[k] : 1.0);
-    cA[k] = (float)(-2.0 * gd / den);
-    cB[k] = (float)(gd * num / (den * den));
-  }
-  if (threadIdx.x == 0) cCE = (g_ce && labels && !is_prob) ? g_ce[0] * w_ce / (float)((double)B * g.Z * g.Y * g.X) : 0.f;
-  __syncthreads();
+// Adjoint of the trilinear interpolation (align_corners=False), gather form: one thread group per COARSE cell sums
+// weight * dfine over the (2*scale)^3 loss-grid voxels whose footprint touches the cell.  No atomics, deterministic.
+// dfine is planar [B][K][Z][Y][X]; dsrc has the layout of the coarse source (planar or channels-last).
+__global__ void __launch_bounds__(256) trilinear_adjoint_k(const float* __restrict__ dfine, SrcGeom g, int K, float* __restrict__ dsrc, int G,
+                                                           long long cells) {
+  __shared__ float red[8];
   const int per_block = 256 / G;
-  const long long cell = (long long)blockIdx.x * per_block + threadIdx.x / G;
+  const long long cell = (long long)blockIdx.x * per_block + threadIdx.x / G;  // cell index includes the class: ((b*K + k)*rz + cz)...
   const int gt = threadIdx.x % G;
-  float acc[KT];
-#pragma unroll
-  for (int k = 0; k < KT; ++k) acc[k] = 0.f;
-  int b = 0, cz = 0, cy = 0, cx = 0;
+  float acc = 0.f;
+  int bk = 0, cz = 0, cy = 0, cx = 0;
   if (cell < cells) {
     long long c = cell;
     cx = (int)(c % g.rx); c /= g.rx;
     cy = (int)(c % g.ry); c /= g.ry;
-    cz = (int)(c % g.rz); b = (int)(c / g.rz);
+    cz = (int)(c % g.rz); bk = (int)(c / g.rz);
     const int fz = g.Z / g.rz, fy = g.Y / g.ry, fx = g.X / g.rx;  // integer scale factors (host-checked)
     const int z0 = max(0, cz * fz - fz / 2 - 1), z1 = min(g.Z - 1, cz * fz + (3 * fz) / 2);
     const int y0 = max(0, cy * fy - fy / 2 - 1), y1 = min(g.Y - 1, cy * fy + (3 * fy) / 2);
     const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
     const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
-    const long long S = (long long)g.Z * g.Y * g.X;
+    const float* src = dfine + (long long)bk * g.Z * g.Y * g.X;
     for (int f = gt; f < nz * ny * nx; f += G) {
       const int x = x0 + f % nx, y = y0 + (f / nx) % ny, z = z0 + f / (nx * ny);
       int i0, i1; float l1;
@@ -218,41 +199,20 @@ __global__ void __launch_bounds__(256) class_stats_bwd_gather_k(const float* __r
       lin_src(x, g.sx, g.rx, i0, i1, l1);
       const float wx = (i0 == cx ? 1.f - l1 : 0.f) + (i1 == cx ? l1 : 0.f);
       const float wgt = wz * wy * wx;
-      if (wgt == 0.f) continue;
-      float dl[KT];
-      voxel_dlogits<KT>(src, g, K, b, z, y, x, (long long)b * S + ((long long)z * g.Y + y) * g.X + x, labels, tgt, is_prob, cA, cB, cCE, dl);
-#pragma unroll
-      for (int k = 0; k < KT; ++k) if (k < K) acc[k] += wgt * dl[k];
+      if (wgt != 0.f) acc += wgt * src[((long long)z * g.Y + y) * g.X + x];
     }
   }
-#pragma unroll
-  for (int k = 0; k < KT; ++k) acc[k] = warp_sum(acc[k]);
+  acc = warp_sum(acc);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (G > 32) {
-    if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < KT; ++k) red[wid][k] = acc[k];
-    }
+    if (lane == 0) red[wid] = acc;
     __syncthreads();
-    if (threadIdx.x < K) {
-      float t = 0.f;
-      for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
-      acc[0] = t;
-    }
+    if (threadIdx.x == 0) { acc = 0.f; for (int w = 0; w < 8; ++w) acc += red[w]; }
   }
-  if (cell < cells) {
+  if (cell < cells && ((G > 32) ? threadIdx.x == 0 : lane == 0)) {
     const long long Sr = (long long)g.rz * g.ry * g.rx, sp = ((long long)cz * g.ry + cy) * g.rx + cx;
-    if (G > 32) {
-      if (threadIdx.x < K) {
-        const int k = threadIdx.x;
-        if (g.planar) dsrc[((long long)b * K + k) * Sr + sp] = acc[0]; else dsrc[((long long)b * Sr + sp) * K + k] = acc[0];
-      }
-    } else if (lane == 0) {
-#pragma unroll
-      for (int k = 0; k < KT; ++k) if (k < K) {
-        if (g.planar) dsrc[((long long)b * K + k) * Sr + sp] = acc[k]; else dsrc[((long long)b * Sr + sp) * K + k] = acc[k];
-      }
-    }
+    const int b = bk / K, k = bk % K;
+    if (g.planar) dsrc[((long long)b * K + k) * Sr + sp] = acc; else dsrc[((long long)b * Sr + sp) * K + k] = acc;
   }
 }
 
@@ -272,11 +232,14 @@ __global__ void __launch_bounds__(256) class_stats_bwd_k(const float* __restrict
                                                          const long long* __restrict__ labels, const float* __restrict__ tgt,
                                                          int is_prob, const float* __restrict__ class_w,
                                                          const double* __restrict__ sums, const float* __restrict__ g_ce,
-                                                         const float* __restrict__ g_dice, float w_ce, float w_dice, float* __restrict__ dsrc) {
+                                                         const float* __restrict__ g_dice, float w_ce, float w_dice, float* __restrict__ dsrc,
+                                                         float* __restrict__ fine_out) {
   __shared__ float cA[KT], cB[KT];
   __shared__ float cCE;
   __shared__ float tile[KT][FP_Z * FP_Y * FP_X];
-  const bool direct = (g.rz == g.Z && g.ry == g.Y && g.rx == g.X);
+  // fine_out: write the per-voxel gradient at loss-grid resolution (planar) and leave the adjoint interpolation to
+  // trilinear_adjoint_k (two-stage backward of interpolated sources)
+  const bool direct = (g.rz == g.Z && g.ry == g.Y && g.rx == g.X) || fine_out != nullptr;
   if (threadIdx.x < K) {
     const int k = threadIdx.x;
     const double num = 2.0 * sums[1 + 3 * k] + 1e-5, den = sums[2 + 3 * k] + sums[3 + 3 * k] + 1e-5;
@@ -311,7 +274,8 @@ __global__ void __launch_bounds__(256) class_stats_bwd_k(const float* __restrict
       const long long v = ((long long)z * g.Y + y) * g.X + x;
 #pragma unroll
       for (int k = 0; k < KT; ++k) if (k < K) {
-        if (g.planar) dsrc[((long long)b * K + k) * S + v] = dl[k];
+        if (fine_out) fine_out[((long long)b * K + k) * S + v] = dl[k];
+        else if (g.planar) dsrc[((long long)b * K + k) * S + v] = dl[k];
         else dsrc[((long long)b * S + v) * K + k] = dl[k];
       }
     } else {
@@ -381,25 +345,24 @@ ICL_API int icl_class_stats_fwd(const float* src, int planar, int rz, int ry, in
 ICL_API int icl_class_stats_bwd(const float* src, int planar, int rz, int ry, int rx, int B, int K, int Z, int Y, int X,
                                 const long long* labels, const float* tgt, int is_prob, const float* class_w, const double* sums,
                                 const float* g_ce, const float* g_dice, float w_ce, float w_dice, float* dsrc /* zeroed when interpolated */,
-                                void* stream) {
+                                float* workspace /* B*K*Z*Y*X floats for interpolated sources, or null (then: atomic scatter) */, void* stream) {
   ICL_REQUIRE(K >= 1 && K <= 16, "class_stats: K=%d unsupported (max 16)", K);
   SrcGeom g;
   if (make_geom(g, planar, rz, ry, rx, Z, Y, X)) return -1;
-  const bool direct = rz == Z && ry == Y && rx == X;
-  if (!direct && Z % rz == 0 && Y % ry == 0 && X % rx == 0) {
-    const long long foot = 8LL * (Z / rz) * (Y / ry) * (X / rx);
-    const int G = foot >= 4096 ? 256 : 32;
-    const long long cells = (long long)B * rz * ry * rx;
-    const long long nb = (cells + (256 / G) - 1) / (256 / G);
-#define CALLG(KT) class_stats_bwd_gather_k<KT><<<(unsigned)nb, 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, G, cells)
-    DISPATCH_K(K, CALLG)
-#undef CALLG
-    ICL_LAUNCHED("class_stats_bwd_gather");
-  }
   const long long blocks = (long long)B * cdiv(Z, BT_Z) * cdiv(Y, BT_Y) * cdiv(X, BT_X);
-#define CALL(KT) class_stats_bwd_k<KT><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc)
+  const bool direct = rz == Z && ry == Y && rx == X;
+  float* fine = (!direct && workspace && Z % rz == 0 && Y % ry == 0 && X % rx == 0) ? workspace : nullptr;
+#define CALL(KT) class_stats_bwd_k<KT><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, fine)
   DISPATCH_K(K, CALL)
 #undef CALL
+  if (fine) {
+    icl_count_launch(1);
+    const long long foot = 8LL * (Z / rz) * (Y / ry) * (X / rx);
+    const int G = foot >= 4096 ? 256 : 32;
+    const long long cells = (long long)B * K * rz * ry * rx;
+    const long long nb = (cells + (256 / G) - 1) / (256 / G);
+    trilinear_adjoint_k<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(fine, g, K, dsrc, G, cells);
+  }
   ICL_LAUNCHED("class_stats_bwd");
 }
 

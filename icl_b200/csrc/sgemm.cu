@@ -116,116 +116,212 @@ ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long l
 }
 
 // ------------------------------------------------------------------------------------------
-// skinny NT:  y[m, n] = act( sum_k x[m, k] * W[n, k] + bias[n] ),  m < M <= 16 per pass.
-// x row-major [M, K], W row-major [N, K] (nn.Linear weight).  Block = 4 warps x 4 n each.
+// Skinny GEMMs against a huge fp32 weight (mlp2 = MLP(N, N, N) over the spatial axis, 13 824 x 13 824 at 24^3,
+// networks/unet_3D_icl.py:258-259,267; rows = B*K*heads <= 64).  They stream every weight exactly once, so the bound is
+// HBM — but 16+ FMAs per weight on the CUDA cores would cap them far below it.  The products therefore run on the
+// tensor cores as error-compensated 3xTF32 (hi*hi + lo*hi + hi*lo with hi = tf32(x), lo = tf32(x - hi): ~21 mantissa
+// bits, fp32-level accuracy) via warp-level mma.sync m16n8k8; W fragments come straight from global memory as
+// 128-bit loads (the K index inside a 16-wide block is permuted identically on both operands so that no shuffle is
+// needed), the small activation operand is split once per chunk into shared memory.
 // ------------------------------------------------------------------------------------------
-#define SK_M 16
-#define SK_KC 256
-__global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const float* __restrict__ x, const float* __restrict__ Wt,
-                                                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act) {
-  __shared__ float xs[SK_M][SK_KC];
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int nb = blockIdx.x * 16 + wid * 4;
-  for (int mg = 0; mg < M; mg += SK_M) {
-    float acc[4][SK_M];
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int m = 0; m < SK_M; ++m) acc[j][m] = 0.f;
-    for (int k0 = 0; k0 < K; k0 += SK_KC) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < SK_M * SK_KC; i += 128) {
-        const int m = i / SK_KC, k = i % SK_KC;
-        xs[m][k] = (mg + m < M && k0 + k < K) ? x[(long long)(mg + m) * K + k0 + k] : 0.f;
-      }
-      __syncthreads();
-#pragma unroll 2
-      for (int kk = lane; kk < SK_KC; kk += 32) {
-        const int k = k0 + kk;
-        float wv[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) wv[j] = (k < K && nb + j < N) ? __ldg(&Wt[(long long)(nb + j) * K + k]) : 0.f;
-#pragma unroll
-        for (int m = 0; m < SK_M; ++m) {
-          const float xv = xs[m][kk];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[j][m] = fmaf(wv[j], xv, acc[j][m]);
-        }
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-#pragma unroll
-      for (int m = 0; m < SK_M; ++m) {
-        const float s = warp_sum(acc[j][m]);
-        if (lane == 0 && nb + j < N && mg + m < M) {
-          float v = s + (bias ? bias[nb + j] : 0.f);
-          const long long o = (long long)(mg + m) * N + nb + j;
-          if (pre) pre[o] = v;
-          y[o] = act == 1 ? gelu_erf(v) : v;
-        }
-      }
-  }
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
 }
-ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
-                                  void* stream) {
-  skinny_nt_k<<<cdiv(N, 16), 128, 0, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act);
-  ICL_LAUNCHED("skinny_linear_fwd");
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-// ------------------------------------------------------------------------------------------
-// skinny NN (data gradient):  dx[m, k] += sum_n dy[m, n] * W[n, k].   dx must be zeroed by the
-// caller; the n range is split over blockIdx.y and combined with atomics.
-// ------------------------------------------------------------------------------------------
-#define SN_NC 64
-__global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const float* __restrict__ dy, const float* __restrict__ Wt,
-                                                   float* __restrict__ dx, int n_per) {
-  __shared__ float ds[SK_M][SN_NC];
-  const int k = (blockIdx.x * 128 + threadIdx.x) * 4;
-  const int nbeg = blockIdx.y * n_per, nend = min(N, nbeg + n_per);
-  const bool kvalid = k < K;  // K % 4 == 0 required
-  for (int mg = 0; mg < M; mg += SK_M) {
-    float acc[SK_M][4];
+// skinny NT:  y[m, n] = act( sum_k x[m, k] * W[n, k] + bias[n] ),  M <= 16*MT.  Block = 4 warps x 8 weight rows.
+#define SK_KC 256
+#define SK_LD (SK_KC + 8)  // row stride of the staged activations: 8*g + 4*t + {0,1} -> conflict-free 64-bit fragment loads
+template <int MT>
+__global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const float* __restrict__ x, const float* __restrict__ Wt,
+                                                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act) {
+  extern __shared__ __align__(16) uint32_t sk_smem[];
+  uint32_t* xh = sk_smem;                         // [MT*16][SK_LD] tf32 hi
+  uint32_t* xl = sk_smem + MT * 16 * SK_LD;       // [MT*16][SK_LD] tf32 lo
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int n0 = (blockIdx.x * 4 + wid) * 8;
+  const int nrow = min(n0 + g, N - 1);  // clamp: rows past N are computed but never stored
+  const float* wrow = Wt + (long long)nrow * K;
+  float acc[MT][4];
 #pragma unroll
-    for (int m = 0; m < SK_M; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0.f; }
-    for (int n0 = nbeg; n0 < nend; n0 += SN_NC) {
-      __syncthreads();
-      for (int i = threadIdx.x; i < SK_M * SN_NC; i += 128) {
-        const int m = i / SN_NC, n = i % SN_NC;
-        ds[m][n] = (mg + m < M && n0 + n < nend) ? dy[(long long)(mg + m) * N + n0 + n] : 0.f;
+  for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
+  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < MT * 16 * (SK_KC / 4); i += 128) {
+      const int m = i / (SK_KC / 4), kq = (i % (SK_KC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(x + (long long)m * K + k0 + kq);
+      uint4 h, l;
+      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+      *reinterpret_cast<uint4*>(&xh[m * SK_LD + kq]) = h;
+      *reinterpret_cast<uint4*>(&xl[m * SK_LD + kq]) = l;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int j0 = 0; j0 < SK_KC / 16; j0 += 8) {
+      float4 wv[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int k = k0 + (j0 + u) * 16 + 4 * t;
+        wv[u] = (k < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
-      __syncthreads();
-      if (kvalid) {
-        const int nn = min(SN_NC, nend - n0);
-#pragma unroll 4
-        for (int n = 0; n < nn; ++n) {
-          const float4 w4 = __ldg(reinterpret_cast<const float4*>(&Wt[(long long)(n0 + n) * K + k]));
 #pragma unroll
-          for (int m = 0; m < SK_M; ++m) {
-            const float g = ds[m][n];
-            acc[m][0] = fmaf(g, w4.x, acc[m][0]); acc[m][1] = fmaf(g, w4.y, acc[m][1]);
-            acc[m][2] = fmaf(g, w4.z, acc[m][2]); acc[m][3] = fmaf(g, w4.w, acc[m][3]);
+      for (int u = 0; u < 8; ++u) {
+        const float wf[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+#pragma unroll
+        for (int sidx = 0; sidx < 2; ++sidx) {
+          // MMA k-slot t   <- weight/activation column 16*(j0+u) + 4t + 2*sidx
+          // MMA k-slot t+4 <- column 16*(j0+u) + 4t + 2*sidx + 1
+          uint32_t b0h, b0l, b1h, b1l;
+          split_tf32(wf[2 * sidx], b0h, b0l);
+          split_tf32(wf[2 * sidx + 1], b1h, b1l);
+          const int col = (j0 + u) * 16 + 4 * t + 2 * sidx;
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            const uint2 ah0 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g) * SK_LD + col]);
+            const uint2 ah1 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g + 8) * SK_LD + col]);
+            const uint2 al0 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g) * SK_LD + col]);
+            const uint2 al1 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g + 8) * SK_LD + col]);
+            mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0h, b1h);
+            mma_tf32(acc[mt], al0.x, al1.x, al0.y, al1.y, b0h, b1h);
+            mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0l, b1l);
           }
         }
       }
     }
-    if (kvalid) {
+  }
+  // C fragment: c0 (row g, col 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
 #pragma unroll
-      for (int m = 0; m < SK_M; ++m)
-        if (mg + m < M) {
-          float* dst = dx + (long long)(mg + m) * K + k;
-          atomicAdd(dst + 0, acc[m][0]); atomicAdd(dst + 1, acc[m][1]); atomicAdd(dst + 2, acc[m][2]); atomicAdd(dst + 3, acc[m][3]);
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int m = mt * 16 + g + (i >> 1) * 8, n = n0 + 2 * t + (i & 1);
+      if (m < M && n < N) {
+        float v = acc[mt][i] + (bias ? bias[n] : 0.f);
+        const long long o = (long long)m * N + n;
+        if (pre) pre[o] = v;
+        y[o] = act == 1 ? gelu_erf(v) : v;
+      }
+    }
+}
+ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
+                                  void* stream) {
+  ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0, "skinny_linear_fwd: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
+  const int grid = cdiv(N, 32);
+#define SK_LAUNCH(MT)                                                                                                    \
+  {                                                                                                                      \
+    const size_t smem = (size_t)2 * MT * 16 * SK_LD * 4;                                                                 \
+    static bool cfg = false;                                                                                             \
+    if (!cfg) { cudaFuncSetAttribute(skinny_nt_k<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg = true; } \
+    skinny_nt_k<MT><<<grid, 128, smem, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act);                          \
+  }
+  if (M <= 16) SK_LAUNCH(1) else if (M <= 32) SK_LAUNCH(2) else SK_LAUNCH(4)
+#undef SK_LAUNCH
+  ICL_LAUNCHED("skinny_linear_fwd");
+}
+
+// skinny NN (data gradient):  dx[m, k] += sum_n dy[m, n] * W[n, k],  M <= 16*MT.  dx must be zeroed by the caller; the n
+// range is split over blockIdx.y and combined with atomics.  Warp = 32 output columns (4 MMA column tiles sharing the
+// A fragment: a weight float4 at [n][kb + 4g .. 4g+3] feeds column g of tiles 0..3), block = 4 warps = 128 columns.
+#define SN_NC 256
+#define SN_LD (SN_NC + 4)  // 4*g + t -> conflict-free 32-bit fragment loads
+template <int MT>
+__global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const float* __restrict__ dy, const float* __restrict__ Wt,
+                                                   float* __restrict__ dx, int n_per) {
+  extern __shared__ __align__(16) uint32_t sk_smem[];
+  uint32_t* dh = sk_smem;
+  uint32_t* dl = sk_smem + MT * 16 * SN_LD;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int kb = (blockIdx.x * 4 + wid) * 32;
+  const int kcol = min(kb + 4 * g, K - 4);  // clamp (K % 4 == 0): columns past K are computed but never stored
+  const int nbeg = blockIdx.y * n_per, nend = min(N, nbeg + n_per);
+  float acc[MT][4][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[mt][j][0] = acc[mt][j][1] = acc[mt][j][2] = acc[mt][j][3] = 0.f;
+  for (int n0 = nbeg; n0 < nend; n0 += SN_NC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < MT * 16 * SN_NC; i += 128) {
+      const int m = i / SN_NC, n = i % SN_NC;
+      const float v = (m < M && n0 + n < nend) ? dy[(long long)m * N + n0 + n] : 0.f;
+      split_tf32(v, dh[m * SN_LD + n], dl[m * SN_LD + n]);
+    }
+    __syncthreads();
+    const int steps = min(SN_NC, nend - n0 + 7) / 8;  // rows past nend multiply zeroed dy (weights clamped in range)
+#pragma unroll 1
+    for (int s0 = 0; s0 < steps; s0 += 4) {
+      float4 w0[4], w1[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int r0 = min(n0 + (s0 + u) * 8 + t, N - 1), r1 = min(n0 + (s0 + u) * 8 + t + 4, N - 1);
+        w0[u] = __ldg(reinterpret_cast<const float4*>(Wt + (long long)r0 * K + kcol));
+        w1[u] = __ldg(reinterpret_cast<const float4*>(Wt + (long long)r1 * K + kcol));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (s0 + u >= steps) break;
+        const int nl = (s0 + u) * 8;
+        const float f0[4] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w}, f1[4] = {w1[u].x, w1[u].y, w1[u].z, w1[u].w};
+        uint32_t ah[MT][4], al[MT][4];
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+          ah[mt][0] = dh[(mt * 16 + g) * SN_LD + nl + t];     ah[mt][1] = dh[(mt * 16 + g + 8) * SN_LD + nl + t];
+          ah[mt][2] = dh[(mt * 16 + g) * SN_LD + nl + t + 4]; ah[mt][3] = dh[(mt * 16 + g + 8) * SN_LD + nl + t + 4];
+          al[mt][0] = dl[(mt * 16 + g) * SN_LD + nl + t];     al[mt][1] = dl[(mt * 16 + g + 8) * SN_LD + nl + t];
+          al[mt][2] = dl[(mt * 16 + g) * SN_LD + nl + t + 4]; al[mt][3] = dl[(mt * 16 + g + 8) * SN_LD + nl + t + 4];
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t b0h, b0l, b1h, b1l;
+          split_tf32(f0[j], b0h, b0l);
+          split_tf32(f1[j], b1h, b1l);
+#pragma unroll
+          for (int mt = 0; mt < MT; ++mt) {
+            mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], b0h, b1h);
+            mma_tf32(acc[mt][j], al[mt][0], al[mt][1], al[mt][2], al[mt][3], b0h, b1h);
+            mma_tf32(acc[mt][j], ah[mt][0], ah[mt][1], ah[mt][2], ah[mt][3], b0l, b1l);
+          }
+        }
+      }
     }
   }
+  // tile j, C fragment column c (= 2t, 2t+1) is the output column kb + 4*c + j
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = mt * 16 + g + (i >> 1) * 8, k = kb + 4 * (2 * t + (i & 1)) + j;
+        if (m < M && k < K) atomicAdd(dx + (long long)m * K + k, acc[mt][j][i]);
+      }
 }
 ICL_API int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream) {
-  ICL_REQUIRE(K % 4 == 0, "skinny_linear_dgrad: K=%d must be a multiple of 4", K);
-  const int gx = cdiv(K, 512);
-  int splits = max(1, min(cdiv(N, SN_NC), (148 * 4) / gx));
+  ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0 && K >= 4, "skinny_linear_dgrad: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
+  const int gx = cdiv(K, 128);
+  int splits = max(1, min(cdiv(N, SN_NC), (148 * 6) / gx));
   const int n_per = cdiv(cdiv(N, splits), SN_NC) * SN_NC;
   splits = cdiv(N, n_per);
-  skinny_nn_k<<<dim3(gx, splits), 128, 0, as_stream(stream)>>>(M, N, K, dy, Wt, dx, n_per);
+#define SN_LAUNCH(MT)                                                                                                    \
+  {                                                                                                                      \
+    const size_t smem = (size_t)2 * MT * 16 * SN_LD * 4;                                                                 \
+    static bool cfg = false;                                                                                             \
+    if (!cfg) { cudaFuncSetAttribute(skinny_nn_k<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg = true; } \
+    skinny_nn_k<MT><<<dim3(gx, splits), 128, smem, as_stream(stream)>>>(M, N, K, dy, Wt, dx, n_per);                      \
+  }
+  if (M <= 16) SN_LAUNCH(1) else if (M <= 32) SN_LAUNCH(2) else SN_LAUNCH(4)
+#undef SN_LAUNCH
   ICL_LAUNCHED("skinny_linear_dgrad");
 }
 

@@ -69,7 +69,7 @@ def _half_bwd(h, dA, need_dx):
     cins = [s.C for s in h.srcs]
     cout = h.w.shape[0]
     B, D, H, W, _ = h.y.shape
-    dgrad_umma = need_dx and ops.umma_ok([cout], sum(cins)) and all(c % 16 == 0 for c in cins)
+    dgrad_umma = need_dx and ops.umma_ok([cout], sum(cins), with_stats=False) and all(c % 16 == 0 for c in cins)
     wgrad_umma = ops.wgrad_umma_ok(cins, cout) and all(s.pk is not None for s in h.srcs)
     if wgrad_umma:
         # fp32 dY is only read by the CUDA-core data-gradient fallback

@@ -49,12 +49,12 @@ def pk_ok(C):
 # conv 3x3x3
 # ------------------------------------------------------------------------------------------
 
-def umma_ok(cins, cout):
+def umma_ok(cins, cout, with_stats=True):
     """Shapes the tcgen05 implicit-GEMM kernel takes; everything else runs the fp32 CUDA-core kernel.
     ICL_DISABLE_UMMA=1 is a debugging knob that routes every conv to the CUDA-core kernel."""
     if os.environ.get("ICL_DISABLE_UMMA") == "1":
         return False
-    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and cout <= 256
+    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and (cout <= 256 or not with_stats)
 
 
 _MAX_CTAS = 0  # 0 = one CTA per SM; tests may lower it to exercise the persistent tile loop
@@ -251,9 +251,9 @@ def linear_fwd(x2d, w, b, act=0, want_pre=False):
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     pre = torch.empty_like(y) if want_pre else None
-    if M <= 16 and K >= 1024:
+    if M <= 64 and K >= 1024 and K % 4 == 0:
         call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act),
-             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K)
+             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
     else:
         sgemm(M, N, K, x2d, K, 1, w, 1, K, y, N, 1, bias=b, bias_mode=1 if b is not None else 0, act=act, pre=pre)
     return y, pre
@@ -262,10 +262,10 @@ def linear_fwd(x2d, w, b, act=0, want_pre=False):
 def linear_dgrad(dy2d, w):
     M, N = dy2d.shape
     K = w.shape[1]
-    if M <= 16 and N >= 1024 and K % 4 == 0:
+    if M <= 64 and N >= 1024 and K % 4 == 0:
         dx = torch.zeros((M, K), dtype=torch.float32, device=dy2d.device)
         call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), mbytes=4e-6 * (N * K + M * K + M * N),
-             gflop=2e-9 * M * N * K)
+             gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
     else:
         dx = torch.empty((M, K), dtype=torch.float32, device=dy2d.device)
         sgemm(M, K, N, dy2d, N, 1, w, K, 1, dx, K, 1)

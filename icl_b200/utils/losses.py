@@ -59,10 +59,11 @@ class _ClassStatsFn(torch.autograd.Function):
             return None, None, None, None, None, None
         direct = (rz, ry, rx) == (Z, Y, X)
         ds = torch.empty_like(s) if direct else torch.zeros_like(s)
+        ws = None if direct else torch.empty(B * K * Z * Y * X, dtype=torch.float32, device=s.device)
         gc = None if g_ce is None else g_ce.detach().float().contiguous()
         gd = None if g_dice is None else g_dice.detach().float().contiguous()
         call("icl_class_stats_bwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
-             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(gc), P(gd), c_f(1.0), c_f(1.0), P(ds))
+             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(gc), P(gd), c_f(1.0), c_f(1.0), P(ds), P(ws))
         return ds, None, None, None, None, None
 
 

@@ -112,7 +112,7 @@ int icl_class_stats_fwd(const float* src, int planar, int rz, int ry, int rx, in
                         const float* tgt, int is_prob, const float* class_w, double* sums, float* out2, void* stream);
 int icl_class_stats_bwd(const float* src, int planar, int rz, int ry, int rx, int B, int K, int Z, int Y, int X, const long long* labels,
                         const float* tgt, int is_prob, const float* class_w, const double* sums, const float* g_ce, const float* g_dice,
-                        float w_ce, float w_dice, float* dsrc, void* stream);
+                        float w_ce, float w_dice, float* dsrc, float* workspace, void* stream);
 int icl_softmax_mse(const float* a, const float* b, int B, int K, long long S, double* sum, const float* gup, float w, float* da, void* stream);
 int icl_scale_to_float(const double* s, double scale, float* out, void* stream);
 
