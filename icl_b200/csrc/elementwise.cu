@@ -143,8 +143,37 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
   const long long n = (s1 - s0) * C;
   const float* dAb = dA + ((long long)b * S + s0) * C;
   const float* yb = y + ((long long)b * S + s0) * C;
-  // When blockDim % C == 0 every thread keeps a fixed channel -> accumulate in registers.
-  if (blockDim.x % C == 0) {
+  // C % 4 == 0 and (4 * blockDim) % C == 0: every thread keeps a fixed group of 4 channels and streams float4s.
+  if (C % 4 == 0 && (4 * blockDim.x) % C == 0) {
+    const int c = (threadIdx.x * 4) % C;
+    float m[4], r[4], sg[4] = {0.f, 0.f, 0.f, 0.f}, sgy[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { m[j] = mr[((long long)b * C + c + j) * 2]; r[j] = mr[((long long)b * C + c + j) * 2 + 1]; }
+    const long long n4 = n >> 2;
+    const float4* y4 = reinterpret_cast<const float4*>(yb);
+    const float4* d4 = reinterpret_cast<const float4*>(dAb);
+#pragma unroll 4
+    for (long long i = threadIdx.x; i < n4; i += blockDim.x) {
+      const float4 yv = y4[i], dv = d4[i];
+      const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, da[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float yh = (ya[j] - m[j]) * r[j];
+        const float g = yh > 0.f ? da[j] : 0.f;
+        sg[j] += g; sgy[j] += g * yh;
+      }
+    }
+    // lanes l and l + C/4 own the same channels: combine them by shuffles first (the shared double atomics are CAS loops)
+    const int P4 = C >> 2;
+    for (int o = 16; o >= P4; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o); sgy[j] += __shfl_xor_sync(0xffffffffu, sgy[j], o); }
+    }
+    if ((int)(threadIdx.x & 31) < P4 || P4 >= 32) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { atomicAdd(&sm[c + j], (double)sg[j]); atomicAdd(&sm[C + c + j], (double)sgy[j]); }
+    }
+  } else if (blockDim.x % C == 0) {
     const int c = threadIdx.x % C;
     const float m = mr[((long long)b * C + c) * 2], r = mr[((long long)b * C + c) * 2 + 1];
     float sg = 0.f, sgy = 0.f;

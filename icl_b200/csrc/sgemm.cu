@@ -33,19 +33,34 @@ __global__ void __launch_bounds__(256) sgemm_k(
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
   const bool a_kfast = (sak == 1), b_nfast = (sbn == 1);
-  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+  // register double buffering: the global loads of K-step i+1 are in flight while step i is multiplied
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int m, k;
       if (a_kfast) { k = t % GK; m = t / GK + 16 * j; } else { m = t % GM; k = t / GM + 4 * j; }
       const int gm = m0 + m, gk = k0 + k;
-      As[k][m] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
+      ra[j] = (gm < M && gk < kend) ? A[gm * sam + gk * sak] : 0.f;
       int n, kb;
       if (b_nfast) { n = t % GN; kb = t / GN + 4 * j; } else { kb = t % GK; n = t / GK + 16 * j; }
       const int gn = n0 + n, gkb = k0 + kb;
-      Bs[kb][n] = (gn < N && gkb < kend) ? Bm[gkb * sbk + gn * sbn] : 0.f;
+      rb[j] = (gn < N && gkb < kend) ? Bm[gkb * sbk + gn * sbn] : 0.f;
+    }
+  };
+  if (kbeg < kend) fetch(kbeg);
+  for (int k0 = kbeg; k0 < kend; k0 += GK) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int m, k;
+      if (a_kfast) { k = t % GK; m = t / GK + 16 * j; } else { m = t % GM; k = t / GM + 4 * j; }
+      As[k][m] = ra[j];
+      int n, kb;
+      if (b_nfast) { n = t % GN; kb = t / GN + 4 * j; } else { kb = t % GK; n = t / GK + 16 * j; }
+      Bs[kb][n] = rb[j];
     }
     __syncthreads();
+    if (k0 + GK < kend) fetch(k0 + GK);
 #pragma unroll
     for (int k = 0; k < GK; ++k) {
       const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
@@ -96,9 +111,9 @@ ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long l
   // few output tiles + long reduction (weight gradients of 1x1x1 convs / Linears over all voxels): split K over the SMs
   const long long tiles = (long long)grid.x * grid.y * batch;
   int ksplit = 1, k_per = K;
-  if (tiles < 148 && K >= 4096 && act == 0 && pre == nullptr) {
+  if (tiles < 148 && K >= 512 && act == 0 && pre == nullptr) {
     ksplit = (int)((148 * 4 + tiles - 1) / tiles);
-    if (ksplit > K / 1024) ksplit = K / 1024;
+    if (ksplit > K / 256) ksplit = K / 256;
     if ((long long)batch * ksplit > 65535) ksplit = 65535 / batch;
     k_per = cdiv(cdiv(K, ksplit), GK) * GK;
     ksplit = cdiv(K, k_per);
@@ -140,8 +155,9 @@ __device__ __forceinline__ void mma_tf32(float* c, uint32_t a0, uint32_t a1, uin
 }
 
 // skinny NT:  y[m, n] = act( sum_k x[m, k] * W[n, k] + bias[n] ),  M <= 16*MT.  Block = 4 warps x 8 weight rows.
+// A lane reads 32 contiguous bytes of its weight row per 32-wide K block (4 lanes = one 128-byte line per row).
 #define SK_KC 256
-#define SK_LD (SK_KC + 8)  // row stride of the staged activations: 8*g + 4*t + {0,1} -> conflict-free 64-bit fragment loads
+#define SK_LD (SK_KC + 2)  // row stride = 2 (mod 32) words: 2*g + 8*t + {0,1} -> conflict-free 64-bit fragment loads
 template <int MT>
 __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const float* __restrict__ x, const float* __restrict__ Wt,
                                                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act) {
@@ -163,29 +179,32 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
       if (m < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(x + (long long)m * K + k0 + kq);
       uint4 h, l;
       split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
-      *reinterpret_cast<uint4*>(&xh[m * SK_LD + kq]) = h;
-      *reinterpret_cast<uint4*>(&xl[m * SK_LD + kq]) = l;
+      *reinterpret_cast<uint2*>(&xh[m * SK_LD + kq]) = make_uint2(h.x, h.y);
+      *reinterpret_cast<uint2*>(&xh[m * SK_LD + kq + 2]) = make_uint2(h.z, h.w);
+      *reinterpret_cast<uint2*>(&xl[m * SK_LD + kq]) = make_uint2(l.x, l.y);
+      *reinterpret_cast<uint2*>(&xl[m * SK_LD + kq + 2]) = make_uint2(l.z, l.w);
     }
     __syncthreads();
 #pragma unroll 1
-    for (int j0 = 0; j0 < SK_KC / 16; j0 += 8) {
-      float4 wv[8];
+    for (int j0 = 0; j0 < SK_KC / 32; j0 += 4) {
+      float4 wv[4][2];
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int k = k0 + (j0 + u) * 16 + 4 * t;
-        wv[u] = (k < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u = 0; u < 4; ++u) {
+        const int k = k0 + (j0 + u) * 32 + 8 * t;
+        wv[u][0] = (k < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u][1] = (k + 4 < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const float wf[4] = {wv[u].x, wv[u].y, wv[u].z, wv[u].w};
+      for (int u = 0; u < 4; ++u) {
+        const float wf[8] = {wv[u][0].x, wv[u][0].y, wv[u][0].z, wv[u][0].w, wv[u][1].x, wv[u][1].y, wv[u][1].z, wv[u][1].w};
 #pragma unroll
-        for (int sidx = 0; sidx < 2; ++sidx) {
-          // MMA k-slot t   <- weight/activation column 16*(j0+u) + 4t + 2*sidx
-          // MMA k-slot t+4 <- column 16*(j0+u) + 4t + 2*sidx + 1
+        for (int sidx = 0; sidx < 4; ++sidx) {
+          // MMA k-slot t   <- weight/activation column 32*(j0+u) + 8t + 2*sidx
+          // MMA k-slot t+4 <- column 32*(j0+u) + 8t + 2*sidx + 1
           uint32_t b0h, b0l, b1h, b1l;
           split_tf32(wf[2 * sidx], b0h, b0l);
           split_tf32(wf[2 * sidx + 1], b1h, b1l);
-          const int col = (j0 + u) * 16 + 4 * t + 2 * sidx;
+          const int col = (j0 + u) * 32 + 8 * t + 2 * sidx;
 #pragma unroll
           for (int mt = 0; mt < MT; ++mt) {
             const uint2 ah0 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g) * SK_LD + col]);
@@ -381,6 +400,8 @@ ICL_API int icl_outer_wgrad(int M, int N, int K, const float* dy, const float* x
   ICL_REQUIRE(M >= 1 && M <= 64, "outer_wgrad: M=%d out of range [1,64]", M);
   dim3 grid(cdiv(K, 256), cdiv(N, 16));
   ICL_REQUIRE(grid.y <= 65535, "outer_wgrad: N too large");
+  static bool cfg = false;
+  if (!cfg) { cudaFuncSetAttribute(outer_wgrad_k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * (16 + 256) * (int)sizeof(float)); cfg = true; }
   outer_wgrad_k<<<grid, 256, (size_t)M * (16 + 256) * sizeof(float), as_stream(stream)>>>(M, N, K, dy, x, dW, db, accumulate);
   ICL_LAUNCHED("outer_wgrad");
 }

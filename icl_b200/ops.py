@@ -187,7 +187,7 @@ def instnorm_relu_bwd(dA, y, mr, want_pk, want_dbias=False, want_f32=True):
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
     db = torch.zeros((C,), dtype=torch.float32, device=y.device) if want_dbias else None
     call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), P(db), c_int(B), c_int(C),
-         c_ll(D * H * W), mbytes=1e-6 * y.numel() * (16 + (4 if want_f32 else 0) + (2 * planes() if want_pk else 0)))
+         c_ll(D * H * W), tag="B%d r%d C%d" % (B, D, C), mbytes=1e-6 * y.numel() * (16 + (4 if want_f32 else 0) + (2 * planes() if want_pk else 0)))
     return (dY, pk, db) if want_dbias else (dY, pk)
 
 
