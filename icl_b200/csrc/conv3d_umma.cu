@@ -23,6 +23,12 @@
 #include "umma.cuh"
 #include <stdlib.h>
 
+// Optional cycle accounting of the three roles (CTA 0 only; thread-local clock64 deltas, env ICL_UMMA_PROF=1).
+#define PROF_DECL() long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t0_ = 0; const bool prof_on = p.prof != nullptr && blockIdx.x == 0
+#define PROF_T0() do { if (prof_on) prof_t0_ = clock64(); } while (0)
+#define PROF_ADD(i) do { if (prof_on) { const long long n_ = clock64(); prof_acc[i] += n_ - prof_t0_; prof_t0_ = n_; } } while (0)
+#define PROF_FLUSH(lo, hi) do { if (prof_on) for (int i_ = lo; i_ <= hi; ++i_) p.prof[i_] = prof_acc[i_]; } while (0)
+
 #define UM_TH 16
 #define UM_TW 8
 #define UM_HL (UM_TH + 2)
@@ -33,6 +39,7 @@
 #define UM_A_SBO (UM_HW * 16)                      // 160
 #define UM_MAX_STAGES 8
 #define UM_MAX_COUT 256
+#define UM_MAX_ACC 8
 
 struct UmmaConvParams {
   const __nv_bfloat16* wp;  // packed weights [nt][kd][chunk][p][tap9][2][NT][8]
@@ -48,28 +55,47 @@ struct UmmaConvParams {
   long long num_tiles;
   int stages, P;
   int tmem_cols;
-  int dbg;
+  int n_acc;  // TMEM accumulator ring depth (MMA of tile t+n_acc waits for the epilogue of tile t)
+  long long* prof;  // optional [16] cycle counters written by CTA 0 (env ICL_UMMA_PROF=1), else null
 };
 
 struct TileCoord { int nt, b, d, h0, w0; };
-// 32-bit arithmetic only: a 64-bit division costs ~100 dependent instructions and this runs once per tile in each of
-// the three single-thread roles (the host checks num_tiles < 2^31).
-__device__ __forceinline__ TileCoord decode_tile(int t, const UmmaConvParams& p) {
-  TileCoord c;
-  c.nt = t % p.n_tiles; t /= p.n_tiles;
-  c.w0 = (t % p.tiles_w) * UM_TW; t /= p.tiles_w;
-  c.h0 = (t % p.tiles_h) * UM_TH; t /= p.tiles_h;
-  c.d = t % p.D;
-  c.b = t / p.D;
-  return c;
-}
+// Tile t = ((((b * D + d) * tiles_h + th) * tiles_w + tw) * n_tiles + nt), walked with stride gridDim.x (neighbouring CTAs
+// work on neighbouring tiles, so halo planes are re-read from L2).  Integer division is ~200 dependent cycles per call
+// on the single-thread roles, so the mixed-radix digits are advanced with carries instead of being re-derived per tile.
+struct TileWalker {
+  int nt, tw, th, d, b;
+  int snt, stw, sth, sd, sb;
+  __device__ __forceinline__ static void digits(int t, const UmmaConvParams& p, int& nt, int& tw, int& th, int& d, int& b) {
+    nt = t % p.n_tiles; t /= p.n_tiles;
+    tw = t % p.tiles_w; t /= p.tiles_w;
+    th = t % p.tiles_h; t /= p.tiles_h;
+    d = t % p.D;
+    b = t / p.D;
+  }
+  __device__ __forceinline__ TileWalker(int t0, int stride, const UmmaConvParams& p) {
+    digits(t0, p, nt, tw, th, d, b);
+    digits(stride, p, snt, stw, sth, sd, sb);
+  }
+  __device__ __forceinline__ void advance(const UmmaConvParams& p) {
+    nt += snt; int c = nt >= p.n_tiles; nt -= c ? p.n_tiles : 0;
+    tw += stw + c; c = tw >= p.tiles_w; tw -= c ? p.tiles_w : 0;
+    th += sth + c; c = th >= p.tiles_h; th -= c ? p.tiles_h : 0;
+    d += sd + c; c = d >= p.D; d -= c ? p.D : 0;
+    b += sb + c;
+  }
+  __device__ __forceinline__ TileCoord coord() const {
+    TileCoord c; c.nt = nt; c.b = b; c.d = d; c.h0 = th * UM_TH; c.w0 = tw * UM_TW; return c;
+  }
+};
 
 __global__ void __launch_bounds__(192, 1)
 conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const UmmaConvParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * UM_MAX_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * UM_MAX_STAGES + 2 * UM_MAX_ACC];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sstat[UM_MAX_COUT][2];
+  __shared__ float sbias[UM_MAX_COUT + 128];  // Cout <= 256 with statistics, <= 384 for the data gradient (no bias there)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int P = p.P, NT = p.NT, stages = p.stages;
@@ -79,17 +105,18 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
   const uint32_t stage_bytes = a_bytes + b_bytes;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;
   const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[UM_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * UM_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * UM_MAX_STAGES + 2]);
+  const uint32_t tfull0 = smem_u32(&bars[2 * UM_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * UM_MAX_STAGES + UM_MAX_ACC]);
   const int nchunks = (p.C0 + p.C1) / UM_KC;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    for (int a = 0; a < p.n_acc; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA0) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA1) : "memory");
   }
   for (int i = threadIdx.x; i < UM_MAX_COUT * 2; i += blockDim.x) (&sstat[0][0])[i] = 0.f;
+  for (int i = threadIdx.x; i < UM_MAX_COUT + 128; i += blockDim.x) sbias[i] = (p.bias && i < p.Cout) ? p.bias[i] : 0.f;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"((uint32_t)p.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -100,42 +127,51 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
+    // ================================ TMA producer (warp-uniform, one elected lane issues) ================================
+    {
+      PROF_DECL();
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(t, p);
+      TileWalker tw_(blockIdx.x, gridDim.x, p);
+      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x, tw_.advance(p)) {
+        const TileCoord tc = tw_.coord();
         for (int kd = 0; kd < 3; ++kd) {
           const int dz = tc.d + kd - 1;
           if (dz < 0 || dz >= p.D) continue;
           for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
+            PROF_T0(); mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage); PROF_ADD(0);
             const uint32_t sa = smem0 + stage * stage_bytes;
             const uint32_t fb = full0 + 8 * stage;
-            mbar_expect_tx(fb, (p.dbg & 8) ? b_bytes : stage_bytes);
             const int k0 = c * UM_KC;
             const bool src0 = k0 < p.C0;
             const CUtensorMap* map = src0 ? &mapA0 : &mapA1;
             const int C8 = (src0 ? p.C0 : p.C1) / 8;
             const int ch8 = (src0 ? k0 : k0 - p.C0) / 8;
-            for (int pl = 0; pl < P && !(p.dbg & 8); ++pl)
-              tma_load_4d(sa + pl * UM_A_PLANE_BYTES, map, fb, (tc.w0 - 1) * 8, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
             const __nv_bfloat16* wsrc = p.wp + ((((long long)tc.nt * 3 + kd) * nchunks + c) * (long long)(b_bytes / 2));
-            bulk_load(sa + a_bytes, wsrc, b_bytes, fb);
+            if (elect_one()) {
+              mbar_expect_tx(fb, stage_bytes);
+              for (int pl = 0; pl < P; ++pl)
+                tma_load_4d(sa + pl * UM_A_PLANE_BYTES, map, fb, (tc.w0 - 1) * 8, tc.h0 - 1, dz, (pl * p.B + tc.b) * C8 + ch8);
+              bulk_load(sa + a_bytes, wsrc, b_bytes, fb);
+            }
+            __syncwarp();
+            PROF_ADD(1);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
       }
+      if (lane == 0) PROF_FLUSH(0, 1);
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
+    // ================================ MMA issuer (warp-uniform, one elected lane issues) ================================
+    {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
-        const TileCoord tc = decode_tile(t, p);
-        mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, 200 + acc);
+      PROF_DECL();
+      TileWalker tw_(blockIdx.x, gridDim.x, p);
+      for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x, tw_.advance(p)) {
+        const TileCoord tc = tw_.coord();
+        PROF_T0(); mbar_wait(tempty0 + 8 * acc, acc_phase ^ 1, 200 + acc); PROF_ADD(2);
         tc_fence_after();
         const uint32_t tmem_d = tmem_base + (uint32_t)(acc * NT);
         uint32_t accumulate = 0;
@@ -143,32 +179,41 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
           const int dz = tc.d + kd - 1;
           if (dz < 0 || dz >= p.D) continue;
           for (int c = 0; c < nchunks; ++c) {
-            mbar_wait(full0 + 8 * stage, phase, 300 + stage);
-            tc_fence_after();
+            mbar_wait(full0 + 8 * stage, phase, 300 + stage); PROF_ADD(3);
+            tc_fence_after(); PROF_ADD(8);
             const uint32_t sa = smem0 + stage * stage_bytes;
-            const uint32_t sb = sa + a_bytes;
+            // Descriptors differ between MMAs only in the 14-bit start-address field (bits 0..13, units of 16 B):
+            // build the four bases once per stage, then each MMA costs one 32-bit add per operand.
+            const uint64_t a_hi0 = umma_desc(sa, UM_A_LBO, UM_A_SBO), a_lo0 = umma_desc(sa + UM_A_PLANE_BYTES, UM_A_LBO, UM_A_SBO);
+            const uint64_t b_hi0 = umma_desc(sa + a_bytes, NT * 16, 128), b_lo0 = umma_desc(sa + a_bytes + b_plane, NT * 16, 128);
+            const uint32_t b_step = (uint32_t)(NT * 32) >> 4;
+            if (elect_one()) {
 #pragma unroll
-            for (int t9 = 0; t9 < ((p.dbg & 4) ? 1 : 9); ++t9) {
-              const uint32_t aoff = (p.dbg & 64) ? 0u : (uint32_t)(((t9 / 3) * UM_HW + (t9 % 3)) * 16);
-              const uint64_t a_hi = umma_desc(sa + aoff, UM_A_LBO, UM_A_SBO);
-              const uint64_t b_hi = umma_desc(sb + t9 * (NT * 32), NT * 16, 128);
-              const uint32_t tmem_dd = (p.dbg & 32) ? (tmem_base + (uint32_t)((t9 & 1) * NT)) : tmem_d;
-              umma_bf16(tmem_dd, a_hi, b_hi, idesc, accumulate);
-              accumulate = 1;
-              if (P == 2 && !(p.dbg & 16)) {
-                const uint64_t a_lo = umma_desc(sa + UM_A_PLANE_BYTES + aoff, UM_A_LBO, UM_A_SBO);
-                const uint64_t b_lo = umma_desc(sb + b_plane + t9 * (NT * 32), NT * 16, 128);
-                umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
-                umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+              for (int t9 = 0; t9 < 9; ++t9) {
+                const uint32_t aoff = (uint32_t)((t9 / 3) * UM_HW + (t9 % 3));  // (kh * halo_w + kw) * 16 B >> 4
+                const uint64_t a_hi = a_hi0 + aoff, b_hi = b_hi0 + t9 * b_step;
+                umma_bf16(tmem_d, a_hi, b_hi, idesc, accumulate);
+                accumulate = 1;
+                if (P == 2) {
+                  umma_bf16(tmem_d, a_hi, b_lo0 + t9 * b_step, idesc, 1);
+                  umma_bf16(tmem_d, a_lo0 + aoff, b_hi, idesc, 1);
+                }
               }
+              PROF_ADD(9);
+              umma_commit(empty0 + 8 * stage);
             }
-            umma_commit(empty0 + 8 * stage);
+            accumulate = 1;
+            __syncwarp();
+            PROF_ADD(4);
             if (++stage == stages) { stage = 0; phase ^= 1; }
           }
         }
-        umma_commit(tfull0 + 8 * acc);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (elect_one()) umma_commit(tfull0 + 8 * acc);
+        __syncwarp();
+        if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
+        if (prof_on) prof_acc[5] += 1;
       }
+      if (lane == 0) { PROF_FLUSH(2, 5); PROF_FLUSH(8, 9); }
     }
   } else {
     // ================================ epilogue (warps 2..5) ================================
@@ -178,8 +223,11 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
     const int et = threadIdx.x - 64;      // 0..127
     int acc = 0; uint32_t acc_phase = 0;
     int cur_b = -1;
-    for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x) {
-      const TileCoord tc = decode_tile(t, p);
+    PROF_DECL();
+    PROF_T0();
+    TileWalker tw_(blockIdx.x, gridDim.x, p);
+    for (int t = blockIdx.x; t < (int)p.num_tiles; t += gridDim.x, tw_.advance(p)) {
+      const TileCoord tc = tw_.coord();
       if (p.stats && tc.b != cur_b) {
         asm volatile("bar.sync 1, 128;" ::: "memory");
         if (cur_b >= 0) {
@@ -192,7 +240,7 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         asm volatile("bar.sync 1, 128;" ::: "memory");
         cur_b = tc.b;
       }
-      mbar_wait(tfull0 + 8 * acc, acc_phase, 400 + acc);
+      mbar_wait(tfull0 + 8 * acc, acc_phase, 400 + acc); PROF_ADD(6);
       tc_fence_after();
       const int h = tc.h0 + hl, w = tc.w0 + wl;
       const bool valid = h < p.H && w < p.W;
@@ -203,13 +251,13 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
         const int n = tc.nt * NT + c0;  // first global output column of this chunk
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + (p.bias ? p.bias[n + i] : 0.f);
-        if (valid && !(p.dbg & 2)) {
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + sbias[n + i];
+        if (valid) {
           float* dst = (n < p.split) ? p.y0 + vox * p.ld0 + n : p.y1 + vox * p.ld1 + (n - p.split);
 #pragma unroll
           for (int i = 0; i < 16; i += 4) *reinterpret_cast<float4*>(dst + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
         }
-        if (p.stats && !(p.dbg & 1)) {
+        if (p.stats) {
           // column sums over the warp's 32 rows by a transposing butterfly: every exchange halves the number of
           // columns a lane still carries (16 -> 8 -> 4 -> 2 -> 1), 16 shuffles per statistic instead of 80; lane l
           // ends with column (l >> 1): even lanes hold its sum, odd lanes its sum of squares.
@@ -236,8 +284,10 @@ conv3d_umma_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty0 + 8 * acc);
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      PROF_ADD(7);
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
+    if (et == 0) PROF_FLUSH(6, 7);
     if (p.stats) {
       asm volatile("bar.sync 1, 128;" ::: "memory");
       if (cur_b >= 0)
@@ -329,6 +379,7 @@ ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1
                                 void* stream) {
   ICL_REQUIRE(C0 > 0 && C0 % 16 == 0 && C1 % 16 == 0 && Cout % 16 == 0, "conv3d_umma: channels must be multiples of 16 (C0=%d C1=%d Cout=%d)", C0, C1, Cout);
   ICL_REQUIRE(Cout <= UM_MAX_COUT || stats == nullptr, "conv3d_umma: Cout=%d > %d with stats", Cout, UM_MAX_COUT);
+  ICL_REQUIRE(Cout <= UM_MAX_COUT + 128, "conv3d_umma: Cout=%d > %d", Cout, UM_MAX_COUT + 128);
   ICL_REQUIRE(P == 1 || P == 2, "conv3d_umma: P must be 1 or 2");
   ICL_REQUIRE(split % 16 == 0, "conv3d_umma: split must be a multiple of 16");
   UmmaConvParams p;
@@ -340,7 +391,14 @@ ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1
   ICL_REQUIRE(p.NT >= 16 && Cout % p.NT == 0, "conv3d_umma: no N tile for Cout=%d", Cout);
   ICL_REQUIRE(y1 == nullptr || split % 16 == 0, "conv3d_umma: bad split");
   p.n_tiles = Cout / p.NT;
-  { const char* e = getenv("ICL_UMMA_DBG"); p.dbg = e ? atoi(e) : 0; }
+  p.prof = nullptr;
+  static long long* prof_buf = nullptr;
+  const bool prof = getenv("ICL_UMMA_PROF") != nullptr;
+  if (prof) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), as_stream(stream));
+    p.prof = prof_buf;
+  }
   p.tiles_h = cdiv(H, UM_TH); p.tiles_w = cdiv(W, UM_TW);
   p.num_tiles = (long long)B * D * p.tiles_h * p.tiles_w * p.n_tiles;
   ICL_REQUIRE(p.num_tiles < (1LL << 31), "conv3d_umma: too many tiles");
@@ -349,8 +407,10 @@ ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1
   if (stages > UM_MAX_STAGES) stages = UM_MAX_STAGES;
   ICL_REQUIRE(stages >= 2, "conv3d_umma: stage of %zu bytes does not fit twice in shared memory", stage_bytes);
   p.stages = stages;
+  p.n_acc = 512 / p.NT < UM_MAX_ACC ? 512 / p.NT : UM_MAX_ACC;
+  { const char* e = getenv("ICL_UMMA_NACC"); if (e && atoi(e) >= 1 && atoi(e) <= p.n_acc) p.n_acc = atoi(e); }
   int cols = 32;
-  while (cols < 2 * p.NT) cols *= 2;
+  while (cols < p.n_acc * p.NT) cols *= 2;
   p.tmem_cols = cols;
   CUtensorMap m0, m1;
   if (make_pk_map(&m0, pk0, P, B, C0, D, H, W)) return -1;
@@ -368,5 +428,13 @@ ICL_API int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1
   long long grid = p.num_tiles < sms ? p.num_tiles : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   conv3d_umma_k<<<(unsigned)grid, 192, smem, as_stream(stream)>>>(m0, m1, p);
+  if (prof) {
+    long long h[16];
+    cudaStreamSynchronize(as_stream(stream));
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double tiles = h[5] > 0 ? (double)h[5] : 1.0;
+    fprintf(stderr, "[umma prof] CTA0 tiles %lld  per tile clk: producer wait_empty %.0f issue %.0f | mma wait_tempty %.0f wait_full %.0f issue+commit %.0f | "
+                    "epilogue wait_tfull %.0f work %.0f | mma: fence %.0f descs+mma issue %.0f commit %.0f\n", h[5], h[0] / tiles, h[1] / tiles, h[2] / tiles, h[3] / tiles, (h[4] + h[8] + h[9]) / tiles, h[6] / tiles, h[7] / tiles, h[8] / tiles, h[9] / tiles, h[4] / tiles);
+  }
   ICL_LAUNCHED("conv3d_umma_fwd");
 }

@@ -92,13 +92,13 @@ conv3d_wgrad_umma_k(const __grid_constant__ CUtensorMap mapX, const __grid_const
   const uint32_t tmem_base = tmem_base_s;
 
   if (warp == 0) {
-    // ================================ TMA producer ================================
-    if (lane == 0) {
-      int stage = 0; uint32_t phase = 0;
-      for (int it = it0; it < it1; ++it) {
-        const WgItem w = wg_decode(it, p);
-        mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
-        const uint32_t sa = smem0 + stage * stage_bytes, fb = full0 + 8 * stage;
+    // ================================ TMA producer (warp-uniform, one elected lane issues) ================================
+    int stage = 0; uint32_t phase = 0;
+    for (int it = it0; it < it1; ++it) {
+      const WgItem w = wg_decode(it, p);
+      mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
+      const uint32_t sa = smem0 + stage * stage_bytes, fb = full0 + 8 * stage;
+      if (elect_one()) {
         mbar_expect_tx(fb, stage_bytes);
         for (int pl = 0; pl < P; ++pl) {
           // X planes 2*zs-1 .. 2*zs+2 (out-of-range planes / halo rows / halo columns zero-fill)
@@ -106,48 +106,48 @@ conv3d_wgrad_umma_k(const __grid_constant__ CUtensorMap mapX, const __grid_const
           // dY planes 2*zs, 2*zs+1
           tma_load_4d(sa + a_bytes + pl * WG_B_BYTES, &mapY, fb, w.w0 * 8, w.h0, 2 * w.zs, (pl * p.B + w.b) * p.Co8 + co_tile * 2);
         }
-        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
+      __syncwarp();
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
   } else if (warp == 1) {
-    // ================================ MMA issuer ================================
-    if (lane == 0) {
-      // kind::f16, D=f32 (bit 4), A=B=bf16 (bits 7, 10), A and B MN-major (bits 15, 16), N>>3 at bit 17, M>>4 at bit 24
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WG_N >> 3) << 17) |
-                             ((uint32_t)(WG_M >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      uint32_t accumulate = 0;
-      for (int it = it0; it < it1; ++it) {
-        mbar_wait(full0 + 8 * stage, phase, 300 + stage);
-        tc_fence_after();
-        const uint32_t sa = smem0 + stage * stage_bytes, sb = sa + a_bytes;
+    // ================================ MMA issuer (warp-uniform, one elected lane issues) ================================
+    // kind::f16, D=f32 (bit 4), A=B=bf16 (bits 7, 10), A and B MN-major (bits 15, 16), N>>3 at bit 17, M>>4 at bit 24
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(WG_N >> 3) << 17) |
+                           ((uint32_t)(WG_M >> 4) << 24);
+    int stage = 0; uint32_t phase = 0;
+    uint32_t accumulate = 0;
+    for (int it = it0; it < it1; ++it) {
+      mbar_wait(full0 + 8 * stage, phase, 300 + stage);
+      tc_fence_after();
+      const uint32_t sa = smem0 + stage * stage_bytes, sb = sa + a_bytes;
+      // descriptor fields for MN-major / no swizzle: LBO = stride between the two K groups of one MMA (next line of 8 voxels),
+      // SBO = stride between 8-channel MN groups.  Only the start-address field (units of 16 B) changes between MMAs.
+      const uint64_t a_hi0 = umma_desc(sa, WG_HW * 16, WG_A_GRP), a_lo0 = umma_desc(sa + WG_A_BYTES, WG_HW * 16, WG_A_GRP);
+      const uint64_t b_hi0 = umma_desc(sb, WG_TW * 16, WG_B_GRP), b_lo0 = umma_desc(sb + WG_B_BYTES, WG_TW * 16, WG_B_GRP);
+      if (elect_one()) {
 #pragma unroll
         for (int t9 = 0; t9 < WG_TAPS; ++t9) {
-          const uint32_t aoff = (uint32_t)(((t9 / 3) * WG_HW + (t9 % 3)) * 16);
+          const uint32_t aoff = (uint32_t)((t9 / 3) * WG_HW + (t9 % 3));  // in 16-byte units
           const uint32_t tmem_d = tmem_base + (uint32_t)(t9 * WG_N);
-          uint32_t acc = accumulate;
 #pragma unroll
           for (int j = 0; j < WG_TH / 2; ++j) {  // one MMA = K 16 voxels = 2 lines of 8
-            // descriptor fields for MN-major / no swizzle: LBO = stride between the two K groups (next line),
-            // SBO = stride between 8-channel MN groups
-            const uint64_t a_hi = umma_desc(sa + aoff + j * 2 * (WG_HW * 16), WG_HW * 16, WG_A_GRP);
-            const uint64_t b_hi = umma_desc(sb + j * 2 * (WG_TW * 16), WG_TW * 16, WG_B_GRP);
-            umma_bf16(tmem_d, a_hi, b_hi, idesc, acc);
-            acc = 1;
+            const uint32_t ao = aoff + j * 2 * WG_HW, bo = j * 2 * WG_TW;
+            umma_bf16(tmem_d, a_hi0 + ao, b_hi0 + bo, idesc, j == 0 ? accumulate : 1u);
             if (P == 2) {
-              const uint64_t a_lo = umma_desc(sa + WG_A_BYTES + aoff + j * 2 * (WG_HW * 16), WG_HW * 16, WG_A_GRP);
-              const uint64_t b_lo = umma_desc(sb + WG_B_BYTES + j * 2 * (WG_TW * 16), WG_TW * 16, WG_B_GRP);
-              umma_bf16(tmem_d, a_hi, b_lo, idesc, 1);
-              umma_bf16(tmem_d, a_lo, b_hi, idesc, 1);
+              umma_bf16(tmem_d, a_hi0 + ao, b_lo0 + bo, idesc, 1);
+              umma_bf16(tmem_d, a_lo0 + ao, b_hi0 + bo, idesc, 1);
             }
           }
         }
-        accumulate = 1;
         umma_commit(empty0 + 8 * stage);
-        if (++stage == stages) { stage = 0; phase ^= 1; }
       }
-      umma_commit(tfull);
+      __syncwarp();
+      accumulate = 1;
+      if (++stage == stages) { stage = 0; phase ^= 1; }
     }
+    if (elect_one()) umma_commit(tfull);
+    __syncwarp();
   } else {
     // ================================ epilogue (warps 2..5): TMEM -> partial buffer ================================
     const int q = warp & 3;  // TMEM lane quarter of this warp; an M=64 accumulator keeps rows 16q..16q+15 in its lanes 0..15

@@ -46,6 +46,19 @@ __device__ __forceinline__ void bulk_load(uint32_t dst, const void* src, uint32_
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
+// One lane of a fully converged warp.  The single-thread tcgen05 / TMA instructions live on the uniform datapath: issuing
+// them from `if (lane == 0)` code makes the compiler wrap every one in a vector->uniform transfer loop (R2UR + ELECT +
+// BRA.U.ANY, ~50 clk per MMA, measured); warp-uniform control flow with elect.sync around the issue keeps operands in
+// uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
