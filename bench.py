@@ -251,14 +251,18 @@ def main_gpu(a):
 
     # ---- per-kernel breakdown (CUDA events around every launch of our kernels), separate pass in this same run
     prof = None
-    if not a.no_profile and rank == 0:
-        ops.profile_start()
+    if not a.no_profile:
+        # every rank runs the profiled steps (they contain collectives); only rank 0 records events
         nprof = 2
+        if rank == 0:
+            ops.profile_start()
         for _ in range(nprof):
             step(x_dev, y_dev)
         torch.cuda.synchronize()
-        prof = ops.profile_stop(nprof)
-        if a.detail:
+        if rank == 0:
+            prof = ops.profile_stop(nprof)
+    if rank == 0 and prof is not None and a.detail:
+        if True:
             os.makedirs(os.path.dirname(os.path.abspath(a.detail)), exist_ok=True)
             json.dump(prof["detail"], open(a.detail, "w"), indent=1)
 
