@@ -53,7 +53,7 @@ def _half_fwd(srcs, w, b):
     h.srcs, h.w = srcs, w
     h.umma = ops.umma_ok(cins, cout) and all(s.pk is not None for s in srcs)
     if h.umma:
-        h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma(w, False), b, cout, B, D, H, W, stats)
+        h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma(w, False, D), b, cout, B, D, H, W, stats)
     elif ops.stem_ok(cins, cout):
         h.y = ops.conv3d_stem_fwd(srcs[0].f32, w, b, B, D, H, W, stats)
     else:
@@ -85,7 +85,7 @@ def _half_bwd(h, dA, need_dx):
         return dw, db, None
     cin_total = sum(cins)
     if dgrad_umma:
-        wp = ops.pack_w_umma(h.w, True)
+        wp = ops.pack_w_umma(h.w, True, D)
         if len(cins) == 2:
             d0, d1 = ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W, split=cins[0])
             return dw, db, [d0, d1]

@@ -61,8 +61,9 @@ _MAX_CTAS = 0  # 0 = one CTA per SM; tests may lower it to exercise the persiste
 
 
 def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, out=None):
-    """pks: 1 or 2 PK tensors (virtual channel concat).  Returns NDHWC output [B,D,H,W,cout], or a pair
-    (y0 [..,split], y1 [..,cout-split]) when split is given (data gradient of a concatenated input)."""
+    """pks: 1 or 2 PK tensors (virtual channel concat).  wp: packed weights from pack_w_umma (a ("walk", tensor) pair selects
+    the plane-walk kernel).  Returns NDHWC output [B,D,H,W,cout], or a pair (y0 [..,split], y1 [..,cout-split]) when split
+    is given (data gradient of a concatenated input)."""
     dev = pks[0].device
     if split is None:
         y0 = out if out is not None else torch.empty((B, D, H, W, cout), dtype=torch.float32, device=dev)
@@ -73,18 +74,31 @@ def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, o
         ld1, sp = cout - split, split
     pk1 = pks[1] if len(pks) > 1 else None
     c1 = cins[1] if len(cins) > 1 else 0
-    call("icl_conv3d_umma_fwd", P(pks[0]), c_int(cins[0]), P(pk1), c_int(c1), P(wp), P(bias), P(y0), c_int(y0.shape[-1]), P(y1),
-         c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout), c_int(planes()), c_int(_MAX_CTAS),
-         gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W, tag="B%d r%d %s->%d" % (B, D, "+".join(map(str, cins)), cout))
+    walk = isinstance(wp, tuple)
+    call("icl_conv3d_umma_walk_fwd" if walk else "icl_conv3d_umma_fwd", P(pks[0]), c_int(cins[0]), P(pk1), c_int(c1), P(wp[1] if walk else wp),
+         P(bias), P(y0), c_int(y0.shape[-1]), P(y1), c_int(ld1), c_int(sp), P(stats), c_int(B), c_int(D), c_int(H), c_int(W), c_int(cout),
+         c_int(planes()), c_int(_MAX_CTAS), gflop=2e-9 * 27 * sum(cins) * cout * B * D * H * W,
+         tag="B%d r%d %s->%d" % (B, D, "+".join(map(str, cins)), cout))
     return y0 if split is None else (y0, y1)
 
 
-def pack_w_umma(w, dgrad):
-    """torch conv weight [Cout,Cin,3,3,3] -> staged bf16 operand (see conv3d_umma.cu)."""
+def walk_ok(k_total, n, D):
+    """The plane-walk kernel takes thin layers whose packed weights fit in shared memory (ICL_DISABLE_WALK=1 turns it off)."""
+    if os.environ.get("ICL_DISABLE_WALK") == "1":
+        return False
+    return bool(_lib.lib().icl_conv3d_umma_walk_ok(k_total, n, D, planes()))
+
+
+def pack_w_umma(w, dgrad, D=0):
+    """torch conv weight [Cout,Cin,3,3,3] -> staged bf16 operand (conv3d_umma.cu), or ("walk", operand) in the
+    plane-walk layout (conv3d_umma_walk.cu) when the layer qualifies at depth D."""
     cout, cin = w.shape[0], w.shape[1]
-    n = cin if dgrad else cout
+    n, k = (cin, cout) if dgrad else (cout, cin)
+    wp = torch.empty(planes() * n * k * 27, dtype=torch.bfloat16, device=w.device)
+    if D and walk_ok(k, n, D):
+        call("icl_pack_w_walk", P(w), P(wp), c_int(cout), c_int(cin), c_int(1 if dgrad else 0), c_int(planes()))
+        return ("walk", wp)
     nt = _lib.lib().icl_umma_ntile(n)
-    wp = torch.empty(planes() * n * (cout if dgrad else cin) * 27, dtype=torch.bfloat16, device=w.device)
     call("icl_pack_w_umma", P(w), P(wp), c_int(cout), c_int(cin), c_int(1 if dgrad else 0), c_int(nt), c_int(planes()))
     return wp
 

@@ -32,6 +32,14 @@ unsigned long long icl_launch_count(void);
 int icl_conv3d_umma_fwd(const void* pk0, int C0, const void* pk1, int C1, const void* wp, const float* bias, float* y0, int ld0,
                         float* y1, int ld1, int split, double* stats, int B, int D, int H, int W, int Cout, int P, int max_ctas,
                         void* stream);
+/* plane-walk variant for thin layers (Cout <= 48, whole packed layer resident in shared memory): the three depth taps are
+   folded into N and accumulate into a ring of TMEM slots owned by consecutive output planes.  Same arguments as above;
+   weights packed by icl_pack_w_walk; icl_conv3d_umma_walk_ok() says whether a layer qualifies. */
+int icl_conv3d_umma_walk_ok(int Cin_total, int Cout, int D, int P);
+int icl_pack_w_walk(const float* w, void* wp, int Cout, int Cin, int dgrad, int P, void* stream);
+int icl_conv3d_umma_walk_fwd(const void* pk0, int C0, const void* pk1, int C1, const void* wp, const float* bias, float* y0, int ld0,
+                             float* y1, int ld1, int split, double* stats, int B, int D, int H, int W, int Cout, int P, int max_ctas,
+                             void* stream);
 int icl_pack_w_umma(const float* w, void* wp, int Cout, int Cin, int dgrad, int NT, int P, void* stream);
 int icl_umma_ntile(int N);
 /* fp32 CUDA-core path for the Cin=1 stem and channel counts that are not multiples of 16. */

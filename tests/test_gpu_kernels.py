@@ -131,6 +131,64 @@ def test_conv3d_umma_fwd(B, cins, cout, dims, mode, tol):
         icl_b200.set_precision("parity")
 
 
+WALK_CASES = [
+    # B, cins, cout, (D,H,W)     (D >= 16 so that the plane-walk kernel is selected)
+    (1, [16], 16, (16, 16, 8)),       # one column, one segment
+    (2, [16], 16, (40, 32, 24)),      # ring of 32 slots wraps, several segments / samples
+    (1, [16, 32], 16, (24, 16, 16)),  # virtual concat (up1 shape), 3 chunks
+    (1, [16], 32, (18, 24, 12)),      # Cout 32: ring of 16 slots, ragged tiles
+    (1, [32], 32, (20, 12, 12)),
+]
+
+
+@pytest.mark.parametrize("mode,tol", [("parity", 2e-4), ("fast", 3e-2)])
+@pytest.mark.parametrize("B,cins,cout,dims", WALK_CASES)
+def test_conv3d_umma_walk_fwd(B, cins, cout, dims, mode, tol):
+    """plane-walk kernel (depth taps folded into N, TMEM accumulator ring) vs F.conv3d, incl. the fused statistics."""
+    import icl_b200
+    ops = _ops()
+    icl_b200.set_precision(mode)
+    try:
+        D, H, W = dims
+        xs = [torch.randn(B, c, D, H, W, generator=g(i)) for i, c in enumerate(cins)]
+        w = torch.randn(cout, sum(cins), 3, 3, 3, generator=g(9)) * (2.0 / (27 * sum(cins))) ** 0.5
+        b = torch.randn(cout, generator=g(10))
+        ref = F.conv3d(torch.cat(xs, 1).double(), w.double(), b.double(), padding=1)
+        pks = [ops.pack_pk(cl(x)) for x in xs]
+        wp = ops.pack_w_umma(w.cuda(), False, D)
+        assert isinstance(wp, tuple) and wp[0] == "walk"
+        stats = torch.zeros(B, cout, 2, dtype=torch.float64, device="cuda")
+        for max_ctas in (0, 3):  # 3 CTAs: every CTA walks many items, ring + stage phases wrap
+            stats.zero_()
+            old = ops._MAX_CTAS
+            ops._MAX_CTAS = max_ctas
+            try:
+                y = ops.conv3d_umma(pks, cins, wp, b.cuda(), cout, B, D, H, W, stats)
+            finally:
+                ops._MAX_CTAS = old
+            torch.cuda.synchronize()
+            assert_close(uncl(y), ref, tol, "walk fwd %s" % mode)
+            assert_close(stats[..., 0].cpu(), ref.sum((2, 3, 4)), tol, "sum", abs_floor=1e-2 if mode == "parity" else 1.0)
+            assert_close(stats[..., 1].cpu(), (ref ** 2).sum((2, 3, 4)), tol * 3, "sumsq")
+    finally:
+        icl_b200.set_precision("parity")
+
+
+def test_conv3d_umma_walk_dgrad_split():
+    """data gradient of a concatenated input through the plane-walk kernel: N = 48 per plane, two outputs."""
+    ops = _ops()
+    B, cins, cout, D, H, W = 1, [16, 32], 16, 20, 16, 16
+    dy = torch.randn(B, cout, D, H, W, generator=g(5))
+    w = torch.randn(cout, 48, 3, 3, 3, generator=g(6)) * 0.05
+    x = torch.zeros(B, 48, D, H, W, requires_grad=True)
+    F.conv3d(x, w, None, padding=1).backward(dy)
+    wp = ops.pack_w_umma(w.cuda(), True, D)
+    assert isinstance(wp, tuple)
+    d0, d1 = ops.conv3d_umma([ops.pack_pk(cl(dy))], [cout], wp, None, 48, B, D, H, W, split=16)
+    assert_close(uncl(d0), x.grad[:, :16], 2e-4, "walk dgrad skip part")
+    assert_close(uncl(d1), x.grad[:, 16:], 2e-4, "walk dgrad up part")
+
+
 def test_conv3d_umma_persistent_loop_and_dgrad_split():
     """few CTAs => each walks many tiles (ring + accumulator phases wrap); dgrad writes two outputs."""
     ops = _ops()

@@ -42,7 +42,7 @@ def main():
         xs = [torch.randn(B, r, r, r, c, device="cuda", generator=g) for c in cins]
         pks = [ops.pack_pk(x) for x in xs]
         w = torch.randn(cout, sum(cins), 3, 3, 3, device="cuda", generator=g) * 0.05
-        wp = ops.pack_w_umma(w, False)
+        wp = ops.pack_w_umma(w, False, r)
         bias = torch.zeros(cout, device="cuda")
         stats = torch.zeros(B, cout, 2, dtype=torch.float64, device="cuda")
         out = torch.empty(B, r, r, r, cout, device="cuda")
