@@ -17,6 +17,12 @@
 #include "umma.cuh"
 #include <stdlib.h>
 
+// Optional cycle accounting of the roles (CTA 0 only; env ICL_UMMA_PROF=1), see conv3d_umma.cu
+#define PROF_DECL() long long prof_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; long long prof_t0_ = 0; const bool prof_on = p.prof != nullptr && blockIdx.x == 0
+#define PROF_T0() do { if (prof_on) prof_t0_ = clock64(); } while (0)
+#define PROF_ADD(i) do { if (prof_on) { const long long n_ = clock64(); prof_acc[i] += n_ - prof_t0_; prof_t0_ = n_; } } while (0)
+#define PROF_FLUSH(lo, hi) do { if (prof_on) for (int i_ = lo; i_ <= hi; ++i_) p.prof[i_] = prof_acc[i_]; } while (0)
+
 #define WK_TH 16
 #define WK_TW 8
 #define WK_HL (WK_TH + 2)
@@ -24,7 +30,7 @@
 #define WK_A_PLANE_BYTES (2 * WK_HL * WK_HW * 16)  // 5760
 #define WK_A_LBO (WK_HL * WK_HW * 16)
 #define WK_A_SBO (WK_HW * 16)
-#define WK_MAX_STAGES 8
+#define WK_MAX_STAGES 16
 #define WK_MAX_SLOTS 32
 #define WK_MAX_N 48  // columns per output plane (Cout, or Cin for the data gradient)
 
@@ -39,8 +45,9 @@ struct WalkParams {
   int C0, C1, Cout;
   int tiles_h, tiles_w, nseg, seg_len;
   int num_items;
-  int stages, P, slots;
+  int stages, P, slots_log2;
   uint32_t w_bytes;         // resident weights
+  long long* prof;
 };
 
 struct WalkItem { int b, d0, d1, h0, w0; };
@@ -62,26 +69,31 @@ __device__ __forceinline__ void tmem_st16_zero(uint32_t taddr) {
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-__global__ void __launch_bounds__(192, 1)
+#define WK_THREADS 320  // warp 0 producer, warp 1 MMA issuer, warps 2-5 and 6-9: two epilogue groups draining alternate planes
+__global__ void __launch_bounds__(WK_THREADS, 1)
 conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1, const WalkParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * WK_MAX_STAGES + 2 * WK_MAX_SLOTS + 2];
+  __shared__ __align__(8) uint64_t bars[WK_MAX_STAGES + 2 * WK_MAX_SLOTS + 2];
   __shared__ uint32_t tmem_base_s;
   __shared__ float sbias[WK_MAX_N];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int P = p.P, NT = p.Cout, stages = p.stages, R = p.slots;
+  const int P = p.P, NT = p.Cout, stages = p.stages;
+  const int RL = p.slots_log2, R = 1 << RL, RM = R - 1;  // ring size is a power of two: slot = k & RM, phase = (k >> RL) & 1 (no integer division in the roles)
   const uint32_t a_bytes = WK_A_PLANE_BYTES * P;
   const uint32_t smem0 = (smem_u32(smem_raw) + 127u) & ~127u;  // resident weights first, then the A stage ring
   const uint32_t sa0 = smem0 + p.w_bytes;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[WK_MAX_STAGES]);
-  const uint32_t tfull0 = smem_u32(&bars[2 * WK_MAX_STAGES]), tempty0 = smem_u32(&bars[2 * WK_MAX_STAGES + WK_MAX_SLOTS]);
-  const uint32_t wfull = smem_u32(&bars[2 * WK_MAX_STAGES + 2 * WK_MAX_SLOTS]), tready = wfull + 8;
+  // full[s]: TMA landed stage s.  pdone[k % R]: every MMA of the k-th input plane this CTA processed has completed — ONE
+  // tcgen05.commit per plane releases both the plane's smem stages (producer) and the output plane it completes (epilogue).
+  // tempty[k % R]: the epilogue drained and zero-filled the accumulator slot of the k-th output plane.
+  const uint32_t full0 = smem_u32(&bars[0]);
+  const uint32_t pdone0 = smem_u32(&bars[WK_MAX_STAGES]), tempty0 = smem_u32(&bars[WK_MAX_STAGES + WK_MAX_SLOTS]);
+  const uint32_t wfull = smem_u32(&bars[WK_MAX_STAGES + 2 * WK_MAX_SLOTS]), tready = wfull + 8;
   const int nchunks = (p.C0 + p.C1) / 16;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
-    for (int a = 0; a < R; ++a) { mbar_init(tfull0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
+    for (int s = 0; s < stages; ++s) mbar_init(full0 + 8 * s, 1);
+    for (int a = 0; a < R; ++a) { mbar_init(pdone0 + 8 * a, 1); mbar_init(tempty0 + 8 * a, 4); }
     mbar_init(wfull, 1);
     mbar_init(tready, 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -108,13 +120,21 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
       }
     }
     __syncwarp();
-    int stage = 0; uint32_t phase = 0;
+    int stage = 0;
+    int kin = 0;                            // running input-plane counter of this CTA
+    const int ahead = stages / nchunks;     // planes that fit in the stage ring (host guarantees >= 1)
+    PROF_DECL();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const WalkItem w = walk_item(it, p);
       const int z0 = max(0, w.d0 - 1), z1 = min(p.D - 1, w.d1);
-      for (int z = z0; z <= z1; ++z) {
+      for (int z = z0; z <= z1; ++z, ++kin) {
+        PROF_T0();
+        if (kin >= ahead) {                 // the stages about to be refilled were read by input plane kin - ahead
+          const int kp = kin - ahead;
+          mbar_wait(pdone0 + 8 * (kp & RM), (kp >> RL) & 1, 100 + (kp & RM));
+        }
+        PROF_ADD(0);
         for (int c = 0; c < nchunks; ++c) {
-          mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
           const uint32_t sa = sa0 + stage * a_bytes, fb = full0 + 8 * stage;
           const int k0 = c * 16;
           const bool src0 = k0 < p.C0;
@@ -127,10 +147,12 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
               tma_load_4d(sa + pl * WK_A_PLANE_BYTES, map, fb, (w.w0 - 1) * 8, w.h0 - 1, z, (pl * p.B + w.b) * C8 + ch8);
           }
           __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          if (++stage == ahead * nchunks) stage = 0;
         }
+        PROF_ADD(1);
       }
     }
+    if (lane == 0) PROF_FLUSH(0, 1);
   } else if (warp == 1) {
     // ================================ MMA issuer ================================
     const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(128 >> 4) << 24);
@@ -138,9 +160,13 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
     const uint32_t b_lbo = 48u * (uint32_t)NT;      // stride between the two k8 chunks = 3*NT rows of 16 B
     mbar_wait(wfull, 0, 500);
     mbar_wait(tready, 0, 501);   // accumulator ring zero-filled by the epilogue warps
+    const int ring = (stages / nchunks) * nchunks;  // stages actually used (whole planes)
+    int kin = 0;
     tc_fence_after();
     int stage = 0; uint32_t phase = 0;
     int kslot = 0;               // running slot counter of the NEXT output plane whose slot has not been acquired yet
+    PROF_DECL();
+    PROF_T0();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const WalkItem w = walk_item(it, p);
       const int z0 = max(0, w.d0 - 1), z1 = min(p.D - 1, w.d1);
@@ -150,17 +176,19 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         const int dlo = max(w.d0, z - 1), dhi = min(w.d1 - 1, z + 1);  // output planes this input plane feeds
         while (acquired <= dhi) {
           const int k = kbase + (acquired - w.d0);
-          mbar_wait(tempty0 + 8 * (k % R), ((k / R) & 1) ^ 1, 200 + (k % R));
+          mbar_wait(tempty0 + 8 * (k & RM), ((k >> RL) & 1) ^ 1, 200 + (k & RM));
           ++acquired;
         }
+        PROF_ADD(2);
         tc_fence_after();
         // pieces: consecutive ring slots; split where the ring wraps
         const int k_lo = kbase + (dlo - w.d0), n_planes = dhi - dlo + 1;
-        const int s_lo = k_lo % R;
+        const int s_lo = k_lo & RM;
         const int n1 = min(n_planes, R - s_lo), n2 = n_planes - n1;
         const int j_lo = dlo - (z - 1);  // weight column block of the first fed plane
         for (int c = 0; c < nchunks; ++c) {
           mbar_wait(full0 + 8 * stage, phase, 300 + stage);
+          PROF_ADD(3);
           tc_fence_after();
           const uint32_t sa = sa0 + stage * a_bytes;
           const uint64_t a_hi0 = umma_desc(sa, WK_A_LBO, WK_A_SBO), a_lo0 = umma_desc(sa + WK_A_PLANE_BYTES, WK_A_LBO, WK_A_SBO);
@@ -188,42 +216,55 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
                 }
               }
             }
-            umma_commit(empty0 + 8 * stage);
           }
           __syncwarp();
-          if (++stage == stages) { stage = 0; phase ^= 1; }
+          PROF_ADD(4);
+          if (++stage == ring) { stage = 0; phase ^= 1; }
         }
-        // output plane z - 1 is complete after input plane z; the last plane of the volume completes with its own input plane
-        if (elect_one()) {
-          if (z - 1 >= w.d0) umma_commit(tfull0 + 8 * ((kbase + (z - 1 - w.d0)) % R));
-          if (z == z1 && z1 == w.d1 - 1) umma_commit(tfull0 + 8 * ((kbase + (z - w.d0)) % R));
-        }
+        // one commit per input plane: frees its stages and completes output plane z - 1 (and z, for the last plane of the volume)
+        if (elect_one()) umma_commit(pdone0 + 8 * (kin & RM));
         __syncwarp();
+        ++kin;
+        PROF_ADD(8);
+        if (prof_on) prof_acc[5] += 1;
       }
       kslot = kbase + (w.d1 - w.d0);
     }
+    if (lane == 0) { PROF_FLUSH(2, 5); PROF_FLUSH(8, 8); }
   } else {
-    // ================================ epilogue (warps 2..5) ================================
+    // ================================ epilogue (warps 2..5 = group 0, warps 6..9 = group 1) ================================
+    // One output plane is drained by ONE group (4 warps = the 4 TMEM lane quarters); the groups take alternate planes so
+    // that two planes are in flight — the per-plane chain (barrier wake-up, tcgen05.ld, stores, tcgen05.st, arrive) is
+    // latency-bound and was the limiter with a single group.
     const int q = warp & 3;
+    const int grp = (warp - 2) >> 2;
     const int row = q * 32 + lane;
     const int hl = row >> 3, wl = row & 7;
-    // zero-fill the accumulator ring once
-    for (int c0 = 0; c0 < R * NT; c0 += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
-    tmem_wait_st();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(tready);
+    if (grp == 0) {  // zero-fill the accumulator ring once
+      for (int c0 = 0; c0 < R * NT; c0 += 16) tmem_st16_zero(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0);
+      tmem_wait_st();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tready);
+    }
     int kslot = 0;
+    int kin_base = 0;  // input-plane counter of this item's first input plane
+    PROF_DECL();
+    PROF_T0();
     for (int it = blockIdx.x; it < p.num_items; it += gridDim.x) {
       const WalkItem w = walk_item(it, p);
+      const int z0 = max(0, w.d0 - 1), z1 = min(p.D - 1, w.d1);
       const int h = w.h0 + hl, x = w.w0 + wl;
       const bool valid = h < p.H && x < p.W;
       float ssum[WK_MAX_N], ssq[WK_MAX_N];
 #pragma unroll
       for (int i = 0; i < WK_MAX_N; ++i) { ssum[i] = 0.f; ssq[i] = 0.f; }
       for (int d = w.d0; d < w.d1; ++d, ++kslot) {
-        const int slot = kslot % R;
-        mbar_wait(tfull0 + 8 * slot, (kslot / R) & 1, 400 + slot);
+        if ((kslot & 1) != grp) continue;
+        const int slot = kslot & RM;
+        const int kdone = kin_base + (min(d + 1, z1) - z0);  // output plane d is complete after input plane d + 1 (or the last one)
+        mbar_wait(pdone0 + 8 * (kdone & RM), (kdone >> RL) & 1, 400 + slot);
+        PROF_ADD(6);
         tc_fence_after();
         const long long vox = (((long long)w.b * p.D + d) * p.H + h) * p.W + x;
 #pragma unroll
@@ -250,6 +291,7 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(tempty0 + 8 * slot);
+        PROF_ADD(7);
       }
       if (p.stats) {
         // per-thread column sums of the whole segment -> warp (transposing butterfly, see conv3d_umma.cu) -> global
@@ -277,7 +319,10 @@ conv3d_umma_walk_k(const __grid_constant__ CUtensorMap mapA0, const __grid_const
           }
         }
       }
+      PROF_ADD(9);
+      kin_base += z1 - z0 + 1;
     }
+    if (warp == 2 && lane == 0) { PROF_FLUSH(6, 7); PROF_FLUSH(9, 9); }
   }
   tc_fence_before();
   __syncthreads();
@@ -325,7 +370,8 @@ ICL_API int icl_pack_w_walk(const float* w, void* wp, int Cout, int Cin, int dgr
 ICL_API int icl_conv3d_umma_walk_ok(int Cin_total, int Cout, int D, int P) {
   if (Cin_total <= 0 || Cin_total % 16 || Cout % 16 || Cout < 16 || Cout > WK_MAX_N || D < 16) return 0;
   const long long w_bytes = (long long)(Cin_total / 16) * P * 9 * 96 * Cout;
-  return w_bytes + 3LL * P * WK_A_PLANE_BYTES <= 216 * 1024 ? 1 : 0;
+  const long long min_stages = (Cin_total / 16) > 3 ? (Cin_total / 16) : 3;  // at least one whole input plane in the stage ring
+  return (min_stages <= WK_MAX_STAGES && w_bytes + min_stages * P * WK_A_PLANE_BYTES <= 216 * 1024) ? 1 : 0;
 }
 
 static int make_walk_map(CUtensorMap* map, const void* pk, int P, int B, int C, int D, int H, int W) {
@@ -373,7 +419,8 @@ ICL_API int icl_conv3d_umma_walk_fwd(const void* pk0, int C0, const void* pk1, i
   int stages = (int)((216 * 1024 - (long long)p.w_bytes) / ((long long)P * WK_A_PLANE_BYTES));
   if (stages > WK_MAX_STAGES) stages = WK_MAX_STAGES;
   p.stages = stages;
-  p.slots = 512 / Cout < WK_MAX_SLOTS ? 512 / Cout : WK_MAX_SLOTS;
+  p.slots_log2 = 0;
+  while ((2 << p.slots_log2) * Cout <= 512 && (2 << p.slots_log2) <= WK_MAX_SLOTS) ++p.slots_log2;
   CUtensorMap m0, m1;
   if (make_walk_map(&m0, pk0, P, B, C0, D, H, W)) return -1;
   if (C1 > 0) { if (make_walk_map(&m1, pk1, P, B, C1, D, H, W)) return -1; } else m1 = m0;
@@ -386,6 +433,23 @@ ICL_API int icl_conv3d_umma_walk_fwd(const void* pk0, int C0, const void* pk1, i
   }
   int grid = p.num_items < sms ? p.num_items : sms;
   if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
-  conv3d_umma_walk_k<<<(unsigned)grid, 192, smem, as_stream(stream)>>>(m0, m1, p);
+  p.prof = nullptr;
+  static long long* prof_buf = nullptr;
+  const bool prof = getenv("ICL_UMMA_PROF") != nullptr;
+  if (prof) {
+    if (!prof_buf) cudaMalloc(&prof_buf, 16 * sizeof(long long));
+    cudaMemsetAsync(prof_buf, 0, 16 * sizeof(long long), as_stream(stream));
+    p.prof = prof_buf;
+  }
+  conv3d_umma_walk_k<<<(unsigned)grid, WK_THREADS, smem, as_stream(stream)>>>(m0, m1, p);
+  if (prof) {
+    long long h[16];
+    cudaStreamSynchronize(as_stream(stream));
+    cudaMemcpy(h, prof_buf, sizeof(h), cudaMemcpyDeviceToHost);
+    const double n = h[5] > 0 ? (double)h[5] : 1.0;
+    fprintf(stderr, "[walk prof] CTA0 input planes %lld (items %d, seg_len %d, stages %d, slots %d)  per plane clk: producer wait_empty %.0f issue %.0f | "
+                    "mma acquire %.0f wait_full %.0f issue+commit %.0f tfull-commit %.0f | epilogue(grp0) wait_tfull %.0f work %.0f stats %.0f\n",
+            h[5], p.num_items, p.seg_len, p.stages, 1 << p.slots_log2, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[8] / n, h[6] / n, h[7] / n, h[9] / n);
+  }
   ICL_LAUNCHED("conv3d_umma_walk_fwd");
 }
