@@ -189,18 +189,28 @@ __global__ void __launch_bounds__(256) trilinear_adjoint_k(const float* __restri
     const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
     const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
     const float* src = dfine + (long long)bk * g.Z * g.Y * g.X;
-    for (int f = gt; f < nz * ny * nx; f += G) {
-      const int x = x0 + f % nx, y = y0 + (f / nx) % ny, z = z0 + f / (nx * ny);
+    // separable weights, no per-voxel index division: lanes own x positions (contiguous loads), the warps of the group
+    // split z, y is walked serially; 1-D weights are evaluated once per lane (x) / per row (y) / per plane (z).
+    const int glane = gt & 31, gwarp = gt >> 5, gwarps = G >> 5;
+    auto w1d = [](int j, float sc, int n, int c) {
       int i0, i1; float l1;
-      lin_src(z, g.sz, g.rz, i0, i1, l1);
-      const float wz = (i0 == cz ? 1.f - l1 : 0.f) + (i1 == cz ? l1 : 0.f);
-      lin_src(y, g.sy, g.ry, i0, i1, l1);
-      const float wy = (i0 == cy ? 1.f - l1 : 0.f) + (i1 == cy ? l1 : 0.f);
-      lin_src(x, g.sx, g.rx, i0, i1, l1);
-      const float wx = (i0 == cx ? 1.f - l1 : 0.f) + (i1 == cx ? l1 : 0.f);
-      const float wgt = wz * wy * wx;
-      if (wgt != 0.f) acc += wgt * src[((long long)z * g.Y + y) * g.X + x];
+      lin_src(j, sc, n, i0, i1, l1);
+      return (i0 == c ? 1.f - l1 : 0.f) + (i1 == c ? l1 : 0.f);
+    };
+    const int xa = x0 + glane, xb = xa + 32;  // nx <= 2 * scale + 2 <= 64
+    const float wxa = xa <= x1 ? w1d(xa, g.sx, g.rx, cx) : 0.f, wxb = xb <= x1 ? w1d(xb, g.sx, g.rx, cx) : 0.f;
+    for (int z = z0 + gwarp; z <= z1; z += gwarps) {
+      const float wz = w1d(z, g.sz, g.rz, cz);
+      if (wz == 0.f) continue;
+      for (int y = y0; y <= y1; ++y) {
+        const float wzy = wz * w1d(y, g.sy, g.ry, cy);
+        if (wzy == 0.f) continue;
+        const float* row = src + ((long long)z * g.Y + y) * g.X;
+        if (wxa != 0.f) acc += wzy * wxa * row[xa];
+        if (wxb != 0.f) acc += wzy * wxb * row[xb];
+      }
     }
+    (void)nz; (void)ny; (void)nx;
   }
   acc = warp_sum(acc);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;

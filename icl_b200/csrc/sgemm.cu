@@ -102,10 +102,97 @@ __global__ void zero_strided_k(float* __restrict__ C, int M, int N, long long sc
   if (i < (long long)M * N) C[(long long)blockIdx.y * sC + (i / N) * scm + (i % N) * scn] = 0.f;
 }
 
+// ------------------------------------------------------------------------------------------
+// M <= 8 rows (the class-proxy queries: B*K tokens through fc_q / proj / mlp, networks/unet_3D_icl.py:277-280,304-306).
+// The tiled kernel above is a chain of K/16 dependent load->sync->FMA steps (~1.5 us each) for these; here every thread
+// issues all of its loads up front, so a launch costs about one memory latency.
+//   NT: C[m][n] = act(sum_k A[m][k] * W[n][k] + bias[n])   one warp per n, lanes stride k   (A, W rows K-contiguous)
+//   NN: C[m][k] = sum_n A[m][n] * W[n][k]                  one thread per k, n split over blockIdx.y (atomics)
+// ------------------------------------------------------------------------------------------
+#define SM_MAXM 8
+__global__ void __launch_bounds__(256) smallm_nt_k(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ W,
+                                                   float* __restrict__ C, const float* __restrict__ bias, int act, float* __restrict__ pre) {
+  const int lane = threadIdx.x & 31;
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (n >= N) return;
+  float acc[SM_MAXM];
+#pragma unroll
+  for (int m = 0; m < SM_MAXM; ++m) acc[m] = 0.f;
+  const float* w = W + (long long)n * K;
+  if ((K & 3) == 0) {
+    for (int k = lane * 4; k < K; k += 128) {
+      const float4 wv = __ldg(reinterpret_cast<const float4*>(w + k));
+#pragma unroll
+      for (int m = 0; m < SM_MAXM; ++m)
+        if (m < M) {
+          const float4 a = __ldg(reinterpret_cast<const float4*>(A + (long long)m * K + k));
+          acc[m] += a.x * wv.x + a.y * wv.y + a.z * wv.z + a.w * wv.w;
+        }
+    }
+  } else {
+    for (int k = lane; k < K; k += 32) {
+      const float wv = __ldg(w + k);
+#pragma unroll
+      for (int m = 0; m < SM_MAXM; ++m)
+        if (m < M) acc[m] += __ldg(A + (long long)m * K + k) * wv;
+    }
+  }
+#pragma unroll
+  for (int m = 0; m < SM_MAXM; ++m) {
+    if (m >= M) break;
+    float v = warp_sum(acc[m]);
+    if (lane == 0) {
+      v += bias ? bias[n] : 0.f;
+      const long long o = (long long)m * N + n;
+      if (pre) pre[o] = v;
+      C[o] = act == 1 ? gelu_erf(v) : v;
+    }
+  }
+}
+__global__ void __launch_bounds__(128) smallm_nn_k(int M, int N, int K, const float* __restrict__ A, const float* __restrict__ W,
+                                                   float* __restrict__ C, int n_per) {
+  const int k = blockIdx.x * 128 + threadIdx.x;
+  const int nbeg = blockIdx.y * n_per, nend = min(N, nbeg + n_per);
+  if (k >= K) return;
+  float acc[SM_MAXM];
+#pragma unroll
+  for (int m = 0; m < SM_MAXM; ++m) acc[m] = 0.f;
+#pragma unroll 8
+  for (int n = nbeg; n < nend; ++n) {
+    const float wv = __ldg(W + (long long)n * K + k);
+#pragma unroll
+    for (int m = 0; m < SM_MAXM; ++m)
+      if (m < M) acc[m] = fmaf(__ldg(A + (long long)m * N + n), wv, acc[m]);
+  }
+#pragma unroll
+  for (int m = 0; m < SM_MAXM; ++m)
+    if (m < M) {
+      if (gridDim.y > 1) atomicAdd(C + (long long)m * K + k, acc[m]);
+      else C[(long long)m * K + k] = acc[m];
+    }
+}
+
 ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, long long sA, const float* Bm, long long sbk,
                       long long sbn, long long sB, float* C, long long scm, long long scn, long long sC, int batch, const float* bias,
                       int bias_mode, int act, int accumulate, float* pre, void* stream) {
   ICL_REQUIRE(M > 0 && N > 0 && K > 0 && batch > 0 && batch <= 65535, "sgemm: bad sizes M=%d N=%d K=%d batch=%d", M, N, K, batch);
+  if (M <= SM_MAXM && batch == 1 && !accumulate && K >= 32) {
+    // A [M][K] row-major; W given as B[k][n]:  NT when W is [N][K] K-contiguous, NN when W is [K][N] N-contiguous
+    if (sak == 1 && sam == K && sbk == 1 && sbn == K && scn == 1 && scm == N && bias_mode != 2) {
+      smallm_nt_k<<<cdiv(N, 8), 256, 0, as_stream(stream)>>>(M, N, K, A, Bm, C, bias_mode == 1 ? bias : nullptr, act, pre);
+      ICL_LAUNCHED("sgemm_smallm_nt");
+    }
+    if (sak == 1 && sam == K && sbn == 1 && sbk == N && scn == 1 && scm == N && bias_mode == 0 && act == 0 && pre == nullptr) {
+      // reduction axis K of this GEMM runs over the rows of W [K][N]
+      const int gx = cdiv(N, 128);
+      int splits = max(1, min(K / 64, (148 * 4) / gx));
+      const int n_per = cdiv(K, splits);
+      splits = cdiv(K, n_per);
+      if (splits > 1) cudaMemsetAsync(C, 0, sizeof(float) * (size_t)M * N, as_stream(stream));
+      smallm_nn_k<<<dim3(gx, splits), 128, 0, as_stream(stream)>>>(M, K, N, A, Bm, C, n_per);
+      ICL_LAUNCHED("sgemm_smallm_nn");
+    }
+  }
   dim3 grid(cdiv(N, GN), cdiv(M, GM), batch);
   ICL_REQUIRE(grid.y <= 65535, "sgemm: M too large for grid.y");
   // few output tiles + long reduction (weight gradients of 1x1x1 convs / Linears over all voxels): split K over the SMs
@@ -160,7 +247,8 @@ __device__ __forceinline__ void mma_tf32(float* c, uint32_t a0, uint32_t a1, uin
 #define SK_LD (SK_KC + 2)  // row stride = 2 (mod 32) words: 2*g + 8*t + {0,1} -> conflict-free 64-bit fragment loads
 template <int MT>
 __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const float* __restrict__ x, const float* __restrict__ Wt,
-                                                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act) {
+                                                   const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act,
+                                                   int k_per) {
   extern __shared__ __align__(16) uint32_t sk_smem[];
   uint32_t* xh = sk_smem;                         // [MT*16][SK_LD] tf32 hi
   uint32_t* xl = sk_smem + MT * 16 * SK_LD;       // [MT*16][SK_LD] tf32 lo
@@ -171,12 +259,15 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
   float acc[MT][4];
 #pragma unroll
   for (int mt = 0; mt < MT; ++mt) acc[mt][0] = acc[mt][1] = acc[mt][2] = acc[mt][3] = 0.f;
-  for (int k0 = 0; k0 < K; k0 += SK_KC) {
+  // gridDim.y > 1: the K range is split over blockIdx.y (more CTAs in flight to cover HBM latency); partial sums are
+  // combined with atomics into y (zeroed by the host) and bias / activation run in skinny_bias_act_k afterwards.
+  const int kbeg = blockIdx.y * k_per, kend = min(K, kbeg + k_per);
+  for (int k0 = kbeg; k0 < kend; k0 += SK_KC) {
     __syncthreads();
     for (int i = threadIdx.x; i < MT * 16 * (SK_KC / 4); i += 128) {
       const int m = i / (SK_KC / 4), kq = (i % (SK_KC / 4)) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (m < M && k0 + kq < K) v = *reinterpret_cast<const float4*>(x + (long long)m * K + k0 + kq);
+      if (m < M && k0 + kq < kend) v = *reinterpret_cast<const float4*>(x + (long long)m * K + k0 + kq);
       uint4 h, l;
       split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
       *reinterpret_cast<uint2*>(&xh[m * SK_LD + kq]) = make_uint2(h.x, h.y);
@@ -191,8 +282,8 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const int k = k0 + (j0 + u) * 32 + 8 * t;
-        wv[u][0] = (k < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[u][1] = (k + 4 < K) ? __ldg(reinterpret_cast<const float4*>(wrow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u][0] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        wv[u][1] = (k + 4 < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
@@ -226,26 +317,50 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
     for (int i = 0; i < 4; ++i) {
       const int m = mt * 16 + g + (i >> 1) * 8, n = n0 + 2 * t + (i & 1);
       if (m < M && n < N) {
-        float v = acc[mt][i] + (bias ? bias[n] : 0.f);
         const long long o = (long long)m * N + n;
+        if (gridDim.y > 1) { atomicAdd(y + o, acc[mt][i]); continue; }
+        float v = acc[mt][i] + (bias ? bias[n] : 0.f);
         if (pre) pre[o] = v;
         y[o] = act == 1 ? gelu_erf(v) : v;
       }
     }
 }
+__global__ void skinny_bias_act_k(float* __restrict__ y, float* __restrict__ pre, const float* __restrict__ bias, long long total, int N, int act) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float v = y[i] + (bias ? bias[i % N] : 0.f);
+    if (pre) pre[i] = v;
+    y[i] = act == 1 ? gelu_erf(v) : v;
+  }
+}
 ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
                                   void* stream) {
   ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0, "skinny_linear_fwd: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
-  const int grid = cdiv(N, 32);
+  const int gx = cdiv(N, 32);
+  // K split so that ~8 CTAs per SM are in flight (K % 4 == 0 and kend multiples of SK_KC keep the float4 loads aligned)
+  int ksplit = 1, k_per = K;
+  if (K >= 4 * SK_KC && gx < 148 * 8) {
+    ksplit = (148 * 8 + gx - 1) / gx;
+    if (ksplit > K / (2 * SK_KC)) ksplit = K / (2 * SK_KC);
+    if (ksplit > 16) ksplit = 16;
+    if (ksplit < 1) ksplit = 1;
+    k_per = cdiv(cdiv(K, ksplit), SK_KC) * SK_KC;
+    ksplit = cdiv(K, k_per);
+  }
+  if (ksplit > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, as_stream(stream));
+  const dim3 grid(gx, ksplit);
 #define SK_LAUNCH(MT)                                                                                                    \
   {                                                                                                                      \
     const size_t smem = (size_t)2 * MT * 16 * SK_LD * 4;                                                                 \
     static bool cfg = false;                                                                                             \
     if (!cfg) { cudaFuncSetAttribute(skinny_nt_k<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg = true; } \
-    skinny_nt_k<MT><<<grid, 128, smem, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act);                          \
+    skinny_nt_k<MT><<<grid, 128, smem, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act, k_per);                          \
   }
   if (M <= 16) SK_LAUNCH(1) else if (M <= 32) SK_LAUNCH(2) else SK_LAUNCH(4)
 #undef SK_LAUNCH
+  if (ksplit > 1) {
+    icl_count_launch(1);
+    skinny_bias_act_k<<<grid_for((long long)M * N, 256), 256, 0, as_stream(stream)>>>(y, pre, bias, (long long)M * N, N, act);
+  }
   ICL_LAUNCHED("skinny_linear_fwd");
 }
 
