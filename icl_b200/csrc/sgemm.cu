@@ -97,6 +97,17 @@ __global__ void __launch_bounds__(256) sgemm_k(
   }
 }
 
+// bias / activation / pre-activation copy of a split-K result (contiguous [batch][M][N])
+__global__ void sgemm_post_k(float* __restrict__ C, float* __restrict__ pre, const float* __restrict__ bias, int bias_mode, int act,
+                             long long total, int M, int N) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = C[i];
+    if (bias_mode == 1) v += bias[i % N];
+    else if (bias_mode == 2) v += bias[(i / N) % M];
+    if (pre) pre[i] = v;
+    C[i] = act == 1 ? gelu_erf(v) : v;
+  }
+}
 __global__ void zero_strided_k(float* __restrict__ C, int M, int N, long long scm, long long scn, long long sC) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (long long)M * N) C[(long long)blockIdx.y * sC + (i / N) * scm + (i % N) * scn] = 0.f;
@@ -195,25 +206,34 @@ ICL_API int icl_sgemm(int M, int N, int K, const float* A, long long sam, long l
   }
   dim3 grid(cdiv(N, GN), cdiv(M, GM), batch);
   ICL_REQUIRE(grid.y <= 65535, "sgemm: M too large for grid.y");
-  // few output tiles + long reduction (weight gradients of 1x1x1 convs / Linears over all voxels): split K over the SMs
+  // few output tiles: split K over the SMs (slices combine with atomics into a zeroed C); bias / activation / the
+  // pre-activation copy then run in a second tiny pass.  A K loop is a chain of dependent load -> sync -> FMA steps
+  // (~1 us each), so 4 tiles x 14 steps on 4 SMs costs ~30 us where 24 CTAs x 3 steps cost ~5.
   const long long tiles = (long long)grid.x * grid.y * batch;
   int ksplit = 1, k_per = K;
-  if (tiles < 148 && K >= 512 && act == 0 && pre == nullptr) {
-    ksplit = (int)((148 * 4 + tiles - 1) / tiles);
-    if (ksplit > K / 256) ksplit = K / 256;
+  const bool contiguous_c = (scn == 1 && scm == N && (batch == 1 || sC == (long long)M * N));
+  const bool needs_post = (act != 0 || pre != nullptr);
+  if (tiles < 148 && K >= 64 && !accumulate && (!needs_post || contiguous_c)) {
+    ksplit = (int)((148 * 2 + tiles - 1) / tiles);
+    if (ksplit > K / 32) ksplit = K / 32;
     if ((long long)batch * ksplit > 65535) ksplit = 65535 / batch;
+    if (ksplit < 1) ksplit = 1;
     k_per = cdiv(cdiv(K, ksplit), GK) * GK;
     ksplit = cdiv(K, k_per);
   }
+  const bool post = ksplit > 1 && needs_post;
   if (ksplit > 1) {
-    if (!accumulate) {
-      zero_strided_k<<<dim3(cdiv((long long)M * N, 256), batch), 256, 0, as_stream(stream)>>>(C, M, N, scm, scn, sC);
-      icl_count_launch(1);
-    }
+    zero_strided_k<<<dim3(cdiv((long long)M * N, 256), batch), 256, 0, as_stream(stream)>>>(C, M, N, scm, scn, sC);
+    icl_count_launch(1);
     grid.z = batch * ksplit;
   }
-  sgemm_k<<<grid, 256, 0, as_stream(stream)>>>(M, N, K, A, sam, sak, sA, Bm, sbk, sbn, sB, C, scm, scn, sC, bias, bias_mode, act,
-                                               accumulate, pre, ksplit, k_per);
+  sgemm_k<<<grid, 256, 0, as_stream(stream)>>>(M, N, K, A, sam, sak, sA, Bm, sbk, sbn, sB, C, scm, scn, sC, post ? nullptr : bias,
+                                               post ? 0 : bias_mode, post ? 0 : act, accumulate, post ? nullptr : pre, ksplit, k_per);
+  if (post) {
+    icl_count_launch(1);
+    const long long total = (long long)batch * M * N;
+    sgemm_post_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(C, pre, bias, bias_mode, act, total, M, N);
+  }
   ICL_LAUNCHED("sgemm");
 }
 

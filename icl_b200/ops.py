@@ -256,7 +256,7 @@ def sgemm(M, N, K, A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias=None, bias_mode=
           sC=0):
     call("icl_sgemm", c_int(M), c_int(N), c_int(K), P(A), c_ll(sam), c_ll(sak), c_ll(sA), P(Bm), c_ll(sbk), c_ll(sbn), c_ll(sB), P(C),
          c_ll(scm), c_ll(scn), c_ll(sC), c_int(batch), P(bias), c_int(bias_mode), c_int(act), c_int(1 if accumulate else 0), P(pre),
-         gflop=2e-9 * M * N * K * batch, tag="%dx%dx%d b%d" % (M, N, K, batch))
+         gflop=2e-9 * M * N * K * batch, mbytes=4e-6 * batch * (M * K + K * N + M * N), tag="%dx%dx%d b%d" % (M, N, K, batch))
 
 
 def linear_fwd(x2d, w, b, act=0, want_pre=False):
