@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--unfused-optimizer", action="store_true", help="materialise the mlp2 weight gradients (reference-style .grad)")
     ap.add_argument("--detail", default="", help="write the per-(kernel, shape) CUDA-event breakdown to this JSON file")
     return ap.parse_args()
 
@@ -180,8 +181,9 @@ def main_gpu(a):
     net = unet_3D_icl(feature_scale=4, n_classes=K_CLASSES, in_channels=1)
     synth.load_synth(net, 1337)
     net.to(dev).train()
-    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4)
-    dp = parallel.GradAverager(net, world) if world > 1 else None
+    # fused_factored: the 13 824^2 mlp2 weight gradients are applied as rank-32 updates inside the optimizer
+    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4, fused_factored=not a.unfused_optimizer)
+    dp = parallel.GradAverager(net, world, factored=a.unfused_optimizer) if world > 1 else None
     ce_loss, dice_loss = L.CrossEntropyLoss(), L.DiceLoss(K_CLASSES)
     aux_loss, pse_loss = L.AuxLoss3D(K_CLASSES), L.PseudoSoftLoss3D(K_CLASSES)
 

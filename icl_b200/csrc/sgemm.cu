@@ -541,6 +541,76 @@ ICL_API int icl_outer_wgrad(int M, int N, int K, const float* dy, const float* x
   ICL_LAUNCHED("outer_wgrad");
 }
 
+// ------------------------------------------------------------------------------------------
+// Fused rank-R weight gradient + momentum-SGD update for the mlp2 weights:
+//   g[n,k] = sum_r dy[r,n] * x[r,k] + wd * p[n,k];   m = mu * m + g;   p -= lr * m
+// The 764 MB gradient of a 13 824 x 13 824 Linear is never written to or re-read from HBM: per element the kernel
+// reads p and m and writes them back (16 B instead of 4 (dW write) + 8 (grad accumulation) + 20 (SGD)).  Rows are staged
+// through shared memory 32 at a time, so any number of (rank-local or all-gathered) factor rows is accepted.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) sgd_factored_k(int R, int N, int K, const float* __restrict__ dy, const float* __restrict__ x,
+                                                      float* __restrict__ p, float* __restrict__ m, const float* __restrict__ lr_ptr,
+                                                      float mu, float wd) {
+  __shared__ float dys[32 * 16];
+  __shared__ __align__(16) float xs[32 * 256];
+  const int n0 = blockIdx.y * 16, k0 = blockIdx.x * 256;
+  const int kq = (threadIdx.x % 64) * 4, ng = (threadIdx.x / 64) * 4;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  for (int r0 = 0; r0 < R; r0 += 32) {
+    const int rows = min(32, R - r0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < rows * 16; i += 256) {
+      const int r = i / 16, n = i % 16;
+      dys[i] = (n0 + n < N) ? dy[(long long)(r0 + r) * N + n0 + n] : 0.f;
+    }
+    for (int i = threadIdx.x; i < rows * 256; i += 256) {
+      const int r = i / 256, k = i % 256;
+      xs[i] = (k0 + k < K) ? x[(long long)(r0 + r) * K + k0 + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[r * 256 + kq]);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float g = dys[r * 16 + ng + i];
+        acc[i][0] = fmaf(g, xv.x, acc[i][0]); acc[i][1] = fmaf(g, xv.y, acc[i][1]);
+        acc[i][2] = fmaf(g, xv.z, acc[i][2]); acc[i][3] = fmaf(g, xv.w, acc[i][3]);
+      }
+    }
+  }
+  const float lr = lr_ptr[0];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + ng + i;
+    if (n >= N) continue;
+    const long long o = (long long)n * K + k0 + kq;
+    if (k0 + kq + 3 < K && (K & 3) == 0) {
+      float4 pv = *reinterpret_cast<float4*>(p + o), mv = *reinterpret_cast<float4*>(m + o);
+      mv.x = mu * mv.x + acc[i][0] + wd * pv.x; mv.y = mu * mv.y + acc[i][1] + wd * pv.y;
+      mv.z = mu * mv.z + acc[i][2] + wd * pv.z; mv.w = mu * mv.w + acc[i][3] + wd * pv.w;
+      pv.x -= lr * mv.x; pv.y -= lr * mv.y; pv.z -= lr * mv.z; pv.w -= lr * mv.w;
+      *reinterpret_cast<float4*>(m + o) = mv;
+      *reinterpret_cast<float4*>(p + o) = pv;
+    } else {
+      for (int j = 0; j < 4; ++j)
+        if (k0 + kq + j < K) {
+          const float b = mu * m[o + j] + acc[i][j] + wd * p[o + j];
+          m[o + j] = b; p[o + j] -= lr * b;
+        }
+    }
+  }
+}
+ICL_API int icl_sgd_factored(int R, int N, int K, const float* dy, const float* x, float* p, float* m, const float* lr_ptr, float mu, float wd,
+                             void* stream) {
+  ICL_REQUIRE(R >= 1 && N >= 1 && K >= 1, "sgd_factored: bad sizes R=%d N=%d K=%d", R, N, K);
+  dim3 grid(cdiv(K, 256), cdiv(N, 16));
+  ICL_REQUIRE(grid.y <= 65535, "sgd_factored: N too large");
+  sgd_factored_k<<<grid, 256, 0, as_stream(stream)>>>(R, N, K, dy, x, p, m, lr_ptr, mu, wd);
+  ICL_LAUNCHED("sgd_factored");
+}
+
 // column sums: out[n] (+)= sum_m a[m*N + n]   (bias gradients of Linear layers)
 __global__ void colsum_k(const float* __restrict__ a, float* __restrict__ out, long long M, int N, int accumulate, long long m_per) {
   const int n = blockIdx.x * 32 + (threadIdx.x & 31);

@@ -26,6 +26,7 @@ class LinearFn(torch.autograd.Function):
         y, pre = ops.linear_fwd(x2, w_, None if b is None else _c(b.detach()), act, want_pre=bool(act))
         ctx.save_for_backward(x2, w_, pre if act else None)
         ctx.has_bias, ctx.act, ctx.xshape, ctx.w_id = b is not None, act, x.shape, id(w)
+        ctx.w_ref = w  # the Parameter itself: icl_b200.optim.SGD(fused_factored=True) hangs a factor sink on it
         return y.reshape(x.shape[:-1] + (w.shape[0],))
 
     @staticmethod
@@ -38,7 +39,19 @@ class LinearFn(torch.autograd.Function):
         dw = db = None
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dp = parallel.factor_context()
-            if dp["world"] > 1 and ctx.w_id in dp["factored_ids"]:
+            sink = getattr(ctx.w_ref, "_icl_factors", None)
+            if sink is not None:
+                # fused optimizer path: hand the rank-<=rows factors to the optimizer, which forms
+                # dy^T x inside the momentum-SGD update; the 764 MB gradient tensor is never materialised (.grad stays None)
+                if dp["world"] > 1:
+                    gd, xd = parallel.gather_factors(g, x2, dp["group"])
+                    sink.append((gd * (1.0 / dp["world"]), xd))
+                else:
+                    sink.append((g, x2))
+                if ctx.has_bias:
+                    db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
+                    call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))
+            elif dp["world"] > 1 and ctx.w_id in dp["factored_ids"]:
                 # data parallel: exchange the rank-<=rows factors instead of all-reducing the 764 MB dW
                 dw = parallel.averaged_factored_wgrad(g, x2, ops.outer_wgrad_acc, dp["group"])
                 if ctx.has_bias:

@@ -13,10 +13,21 @@ from .ops import P, c_f, c_int, call
 
 
 class SGD(torch.optim.Optimizer):
-    def __init__(self, params, lr=0.01, momentum=0.0, dampening=0, weight_decay=0.0, nesterov=False):
+    def __init__(self, params, lr=0.01, momentum=0.0, dampening=0, weight_decay=0.0, nesterov=False, fused_factored=False,
+                 factored_min_numel=1 << 24):
+        """fused_factored=True: 2-D weights with at least `factored_min_numel` elements (the 13 824^2 mlp2 Linears) never get
+        a materialised .grad — icl_b200.functional.LinearFn hands their rank-<=rows factors (dY, X) to this optimizer, which
+        forms dY^T X inside the update kernel.  Same update rule and numerics as the unfused path up to fp32 summation order."""
         if dampening != 0 or nesterov:
             raise NotImplementedError("icl_b200.optim.SGD implements dampening=0, nesterov=False (the ICL loops' configuration)")
         super().__init__(params, dict(lr=lr, momentum=momentum, weight_decay=weight_decay))
+        self._factored = []
+        if fused_factored:
+            for group in self.param_groups:
+                for p in group["params"]:
+                    if p.dim() == 2 and p.numel() >= factored_min_numel:
+                        p._icl_factors = []
+                        self._factored.append(p)
         self._chunk = _lib.lib().icl_sgd_chunk()
         self._cache = {}
 
@@ -34,6 +45,28 @@ class SGD(torch.optim.Optimizer):
             hit = (ct, co)
             self._cache = {key: hit}
         return hit
+
+    def zero_grad(self, set_to_none=True):
+        for p in self._factored:
+            p._icl_factors.clear()
+        return super().zero_grad(set_to_none=set_to_none)
+
+    def _step_factored(self, group, lr):
+        for p in group["params"]:
+            fs = getattr(p, "_icl_factors", None)
+            if not fs:
+                continue
+            if p.grad is not None:
+                raise RuntimeError("icl_b200.optim.SGD: a fused-factored weight also has a materialised .grad")
+            dy = torch.cat([f[0] for f in fs], 0).contiguous()
+            x = torch.cat([f[1] for f in fs], 0).contiguous()
+            st = self.state[p]
+            if "momentum_buffer" not in st:
+                st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            N, K = p.shape
+            call("icl_sgd_factored", c_int(dy.shape[0]), c_int(N), c_int(K), P(dy), P(x), P(p), P(st["momentum_buffer"]), P(lr),
+                 c_f(group["momentum"]), c_f(group["weight_decay"]), mbytes=16e-6 * p.numel(), tag="R%d %dx%d" % (dy.shape[0], N, K))
+            fs.clear()
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -55,12 +88,15 @@ class SGD(torch.optim.Optimizer):
                 m = st["momentum_buffer"]
                 rows.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel()))
                 keep.append(g)
+            dev = group["params"][0].device
+            lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+            if self._factored:
+                with torch.cuda.device(dev):
+                    self._step_factored(group, lr)
             if not rows:
                 continue
-            dev = group["params"][0].device
             tab = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(dev)
             ct, co = self._chunks([r[3] for r in rows], dev)
-            lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
             with torch.cuda.device(dev):
                 call("icl_sgd_multi", P(tab), P(ct), P(co), c_int(ct.numel()), P(lr), c_f(group["momentum"]), c_f(group["weight_decay"]),
                      c_int(0), mbytes=20e-6 * sum(r[3] for r in rows))

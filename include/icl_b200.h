@@ -128,6 +128,9 @@ int icl_scale_to_float(const double* s, double scale, float* out, void* stream);
 int icl_sgd_multi(const void* tab, const int* chunk_tensor, const long long* chunk_off, int n_chunks, const float* lr_ptr, float mu, float wd,
                   int first, void* stream);
 int icl_sgd_chunk(void);
+/* fused rank-R weight gradient + SGD update for the mlp2 weights: the gradient dy^T x is formed on the fly, never stored */
+int icl_sgd_factored(int R, int N, int K, const float* dy, const float* x, float* p, float* m, const float* lr_ptr, float mu, float wd,
+                     void* stream);
 
 /* ---- sliding-window inference + Dice counts: test_3D_BraTS.py:110-135,175-187 (val_3D.py:43-97) ---- */
 int icl_sw_accumulate(const float* logits, int K, int pw, int ph, int pd, float* score, float* cnt, int W, int H, int D, int xs, int ys, int zs,

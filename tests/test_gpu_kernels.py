@@ -542,6 +542,31 @@ def test_sgd_multi_matches_torch():
         assert_close(b.detach().cpu(), a.detach(), 1e-6, "sgd param")
 
 
+def test_sgd_fused_factored_matches_torch():
+    """fused rank-R weight gradient + SGD (mlp2 path): a Linear whose weight is above the factoring threshold is used twice per
+    step (like mlp2 in the sspa and uscl passes); .grad is never materialised, the update equals torch.optim.SGD's."""
+    import icl_b200.functional as Fn
+    from icl_b200.optim import SGD
+    N, K, M = 70, 52, 9
+    w0 = torch.randn(N, K, generator=g(1)) * 0.2
+    b0 = torch.randn(N, generator=g(2))
+    wr, br = w0.clone().requires_grad_(True), b0.clone().requires_grad_(True)
+    wm, bm = w0.clone().cuda().requires_grad_(True), b0.clone().cuda().requires_grad_(True)
+    o_ref = torch.optim.SGD([wr, br], lr=0.05, momentum=0.9, weight_decay=1e-4)
+    o_mine = SGD([wm, bm], lr=0.05, momentum=0.9, weight_decay=1e-4, fused_factored=True, factored_min_numel=1000)
+    for step in range(3):
+        xa, xb = torch.randn(M, K, generator=g(10 + step)), torch.randn(M + 3, K, generator=g(20 + step))
+        o_ref.zero_grad()
+        (F.linear(xa, wr, br).pow(2).mean() + F.gelu(F.linear(xb, wr, br)).sum() * 0.01).backward()
+        o_ref.step()
+        o_mine.zero_grad()
+        (Fn.linear(xa.cuda(), wm, bm).pow(2).mean() + Fn.linear(xb.cuda(), wm, bm, act=1).sum() * 0.01).backward()
+        assert wm.grad is None and bm.grad is not None
+        o_mine.step()
+    assert_close(wm.detach().cpu(), wr.detach(), 2e-6, "fused factored weight")
+    assert_close(bm.detach().cpu(), br.detach(), 2e-6, "bias")
+
+
 def test_sliding_window_kernels_and_dice_counts():
     from icl_b200 import inference
     K, W, H, D = 3, 20, 18, 17
