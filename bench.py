@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--unfused-optimizer", action="store_true", help="materialise the mlp2 weight gradients (reference-style .grad)")
+    ap.add_argument("--fused-optimizer", action="store_true", help="apply the mlp2 weight gradients as rank-R updates inside the optimizer")
+    ap.add_argument("--no-graph", action="store_true", help="eager step (one Python-enqueued launch per kernel) instead of CUDA-graph replay")
     ap.add_argument("--detail", default="", help="write the per-(kernel, shape) CUDA-event breakdown to this JSON file")
     return ap.parse_args()
 
@@ -182,8 +183,8 @@ def main_gpu(a):
     synth.load_synth(net, 1337)
     net.to(dev).train()
     # fused_factored: the 13 824^2 mlp2 weight gradients are applied as rank-32 updates inside the optimizer
-    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4, fused_factored=not a.unfused_optimizer)
-    dp = parallel.GradAverager(net, world, factored=a.unfused_optimizer) if world > 1 else None
+    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4, fused_factored=a.fused_optimizer)
+    dp = parallel.GradAverager(net, world, factored=not a.fused_optimizer) if world > 1 else None
     ce_loss, dice_loss = L.CrossEntropyLoss(), L.DiceLoss(K_CLASSES)
     aux_loss, pse_loss = L.AuxLoss3D(K_CLASSES), L.PseudoSoftLoss3D(K_CLASSES)
 
@@ -192,15 +193,28 @@ def main_gpu(a):
     x_dev, y_dev = x_host.to(dev), y_host.to(dev)
     it = [0]
 
+    phases = os.environ.get("ICL_BENCH_PHASES") == "1"   # debug: CUDA-event time of forward / losses / backward / optimizer
+    ph_ev = []
+
+    def mark():
+        if phases:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ph_ev.append(e)
+
     def step(volume_batch, label_batch):
+        mark()
         outputs = net(volume_batch[:LABELED_BS], volume_batch[LABELED_BS:])
+        mark()
         loss_ce, loss_dice = L.seg_ce_dice(outputs[0], label_batch[:LABELED_BS])
         loss_aux = aux_loss(outputs[2], label_batch[:LABELED_BS])
         loss_pse = pse_loss(outputs[3], outputs[1])
         loss_cons = L.softmax_mse_loss(outputs[3], outputs[4])
         loss = loss_dice + loss_ce + loss_aux + loss_pse + 10 * loss_cons
         opt.zero_grad(set_to_none=True)
+        mark()
         loss.backward()
+        mark()
         if dp is not None:
             dp.average()
         opt.step()
@@ -208,6 +222,7 @@ def main_gpu(a):
         for g in opt.param_groups:
             g["lr"] = lr_
         it[0] += 1
+        mark()
         return loss
 
     def barrier():
@@ -215,12 +230,16 @@ def main_gpu(a):
             dist.barrier()
         torch.cuda.synchronize()
 
+    host_ms = [0.0]
+
     def timed(fn, n):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        t0 = time.perf_counter()
         for _ in range(n):
             fn()
+        host_ms[0] = (time.perf_counter() - t0) * 1e3 / n   # host time to ENQUEUE one step (no sync inside)
         e1.record()
         barrier()
         ms = e0.elapsed_time(e1)
@@ -230,13 +249,44 @@ def main_gpu(a):
             ms = float(t.item())
         return ms / n
 
+    # ---- CUDA-graph replay of the whole step (single GPU; the eager step is host-bound)
+    use_graph = (not a.no_graph) and world == 1
+    eager_step = step
+    if use_graph:
+        from icl_b200.graph import GraphedStep
+        for _ in range(2):
+            eager_step(x_dev, y_dev)
+        lc0 = _lib.launch_count()
+        graphed = GraphedStep(eager_step, (x_dev, y_dev), opt, warmup=1)
+        # our kernel nodes in the captured graph = C-ABI launches issued by the (1 warm-up + 1 captured) step executions
+        graph_launches_per_step = (_lib.launch_count() - lc0) // 2
+
+        def step(volume_batch, label_batch):  # noqa: F811
+            lr_ = BASE_LR * (1.0 - it[0] / MAX_ITERS) ** 0.9   # the captured step cannot update python state: do it here
+            for g in opt.param_groups:
+                g["lr"] = lr_
+            it[0] += 1
+            return graphed(volume_batch, label_batch)
+
     # ---- device-resident arm
     for _ in range(max(a.warmup, 3)):
         step(x_dev, y_dev)
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = _lib.launch_count()
+    del ph_ev[:]
     ms = timed(lambda: step(x_dev, y_dev), a.steps)
+    host_enqueue_ms = host_ms[0]
     launches = (_lib.launch_count() - l0)
+    if use_graph:
+        launches = graph_launches_per_step * a.steps   # replays do not pass through the C-ABI launch counter
+    if phases and rank == 0:
+        names = ["forward", "losses", "backward", "optimizer"]
+        tot = [0.0] * 4
+        for i in range(0, len(ph_ev) - 4, 5):
+            for j in range(4):
+                tot[j] += ph_ev[i + j].elapsed_time(ph_ev[i + j + 1])
+        n = max(1, len(ph_ev) // 5)
+        sys.stderr.write("[phases] " + "  ".join("%s %.2f ms" % (nm, t / n) for nm, t in zip(names, tot)) + "\n")
     clocks = sampler.stop() if sampler else None
 
     # ---- end-to-end arm: pinned host buffers in, loss scalar out, every step
@@ -259,7 +309,7 @@ def main_gpu(a):
         if rank == 0:
             ops.profile_start()
         for _ in range(nprof):
-            step(x_dev, y_dev)
+            eager_step(x_dev, y_dev)
         torch.cuda.synchronize()
         if rank == 0:
             prof = ops.profile_stop(nprof)
@@ -285,11 +335,11 @@ def main_gpu(a):
             "vs_baseline": None, "dtype": "bf16x3+fp32" if a.precision == "parity" else "bf16+fp32", "data": "synthetic",
             "config": {"workload": "config2: unet_3D_icl(K=2,in=1) ICL train step (fwd + 5 losses + bwd + SGD), per-rank batch 4 "
                                    "(2 lab + 2 unlab) x 1x96^3", "global_batch": BATCH * world, "parallelism": "dp%d" % world,
-                       "precision_mode": a.precision,
+                       "precision_mode": a.precision, "launch": "cuda-graph replay of the whole step" if use_graph else "eager",
                        "l2": "no flush needed: per-step working set (785M params + activations, >15 GB) >> 126 MB L2"},
             "e2e": {"value": vox / (ms_e2e * 1e-3), "unit": "voxels/s", "ms_per_step": ms_e2e,
                     "h2d_bytes_per_step": x_host.numel() * 4 + y_host.numel() * 8, "d2h_bytes_per_step": 4},
-            "gpu_launches": int(launches),
+            "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms,
             "clocks": clocks,
             "conv_tensor_util": {"algorithmic_gflop_per_step": CONV_GFLOP_PER_STEP},
         }

@@ -555,7 +555,8 @@ ICL_API int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, 
 // regenerated identically in backward so no mask is stored.
 // ------------------------------------------------------------------------------------------
 __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ out, const unsigned char* __restrict__ mask,
-                          unsigned long long seed, float p, long long total) {
+                          unsigned long long seed, const unsigned long long* __restrict__ seed_ptr, float p, long long total) {
+  if (seed_ptr) seed = seed_ptr[0];  // seed in device memory: the launch can be captured in a CUDA graph and re-seeded per replay
   const float scale = 1.f / (1.f - p);
   const long long n4 = (total + 3) / 4;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < n4; q += (long long)gridDim.x * blockDim.x) {
@@ -573,10 +574,10 @@ __global__ void dropout_k(const float* __restrict__ x, float* __restrict__ out, 
     }
   }
 }
-ICL_API int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, float p, long long total,
-                        void* stream) {
+ICL_API int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, const unsigned long long* seed_ptr,
+                        float p, long long total, void* stream) {
   ICL_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f out of range", p);
-  dropout_k<<<grid_for((total + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, out, mask, seed, p, total);
+  dropout_k<<<grid_for((total + 3) / 4, 256), 256, 0, as_stream(stream)>>>(x, out, mask, seed, seed_ptr, p, total);
   ICL_LAUNCHED("dropout");
 }
 

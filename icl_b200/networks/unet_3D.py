@@ -43,14 +43,16 @@ class _Backbone3DModule(nn.Module):
 
     def _drop_cfg(self):
         """Dropout(0.3) after `center` and after `up1` (unet_3D_icl.py:110,116): identity unless the Dropout
-        modules are in training mode.  Seeds come from torch's CPU generator (deterministic under manual_seed)."""
+        modules are in training mode.  Seeds come from torch's CUDA generator (deterministic under manual_seed)."""
         if not (self.dropout1.training or self.dropout2.training):
             return None
         if self._mask_queue:
             m1, m2 = self._mask_queue.pop(0), self._mask_queue.pop(0)
             return (self.dropout1.p, m1, m2, 0, 0)
-        s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64)
-        return (self.dropout1.p, None, None, int(s[0]), int(s[1]))
+        # seeds are drawn on the device (torch's CUDA generator: deterministic under manual_seed, no host sync, and the
+        # draw itself is CUDA-graph safe, so every replay of a captured step gets fresh masks)
+        s = torch.randint(0, 2 ** 62, (2,), dtype=torch.int64, device=self.final.weight.device)
+        return (self.dropout1.p, None, None, s[0:1], s[1:2])
 
     def _run(self, x):
         if not x.is_cuda:

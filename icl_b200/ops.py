@@ -243,8 +243,12 @@ def upsample2x_bwd(dout, c_off, C, dx, accumulate):
 
 
 def dropout(x, p, mask=None, seed=0):
+    """seed: python int, or a 1-element int64 CUDA tensor (read by the kernel: no host sync, CUDA-graph capturable)."""
     out = torch.empty_like(x)
-    call("icl_dropout", P(x), P(out), P(mask), c_ull(int(seed) & 0xFFFFFFFFFFFFFFFF), c_f(p), c_ll(x.numel()))
+    if isinstance(seed, torch.Tensor):
+        call("icl_dropout", P(x), P(out), P(mask), c_ull(0), P(seed), c_f(p), c_ll(x.numel()))
+    else:
+        call("icl_dropout", P(x), P(out), P(mask), c_ull(int(seed) & 0xFFFFFFFFFFFFFFFF), P(None), c_f(p), c_ll(x.numel()))
     return out
 
 

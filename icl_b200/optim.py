@@ -30,6 +30,8 @@ class SGD(torch.optim.Optimizer):
                         self._factored.append(p)
         self._chunk = _lib.lib().icl_sgd_chunk()
         self._cache = {}
+        self._lr_dev = {}     # per group: persistent 1-element device tensor the kernels read the learning rate from
+        self._tab_cache = {}  # per group: (key, pinned host table, device table) of (param, grad, momentum) pointers
 
     def _chunks(self, numels, device):
         key = (tuple(numels), str(device))
@@ -68,13 +70,60 @@ class SGD(torch.optim.Optimizer):
                  c_f(group["momentum"]), c_f(group["weight_decay"]), mbytes=16e-6 * p.numel(), tag="R%d %dx%d" % (dy.shape[0], N, K))
             fs.clear()
 
+    def _lr_tensor(self, gi, group, dev):
+        """Learning rate in device memory.  Refreshed from param_groups on every eager step; inside CUDA-graph capture the
+        refresh is skipped (it would bake the value in) — call sync_lr() before each replay instead."""
+        t = self._lr_dev.get(gi)
+        if t is None or t.device != dev:
+            t = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+            self._lr_dev[gi] = t
+        elif not torch.cuda.is_current_stream_capturing():
+            t.fill_(float(group["lr"]))
+        return t
+
+    def sync_lr(self):
+        for gi, group in enumerate(self.param_groups):
+            t = self._lr_dev.get(gi)
+            if t is not None:
+                t.fill_(float(group["lr"]))
+
+    def _table(self, gi, rows, dev):
+        """Device table of (p, g, m, n) rows.  Gradient tensors are re-allocated every step, but the caching allocator (and a
+        CUDA graph's private pool) returns the same addresses, so a table is uploaded only when a pointer set is new — from
+        pinned memory, asynchronously.  Tables are never overwritten (a captured graph keeps replaying its upload), and one
+        spare pinned/device pair is kept ready because pinned memory cannot be allocated during stream capture."""
+        key = tuple(rows)
+        cache = self._tab_cache.setdefault(gi, {"tabs": {}, "spare": None})
+        hit = cache["tabs"].get(key)
+        capturing = torch.cuda.is_current_stream_capturing()
+        if hit is None:
+            shape = (len(rows), 4)
+            sp = cache["spare"]
+            if sp is not None and tuple(sp[0].shape) == shape and sp[1].device == dev:
+                host, tab = sp
+                cache["spare"] = None
+            elif capturing:
+                raise RuntimeError("icl_b200.optim.SGD: run at least one eager step before capturing a CUDA graph")
+            else:
+                host = torch.empty(shape, dtype=torch.int64).pin_memory()
+                tab = torch.empty(shape, dtype=torch.int64, device=dev)
+            host.numpy()[...] = np.asarray(rows, dtype=np.int64)
+            tab.copy_(host, non_blocking=True)
+            if len(cache["tabs"]) >= 8:
+                cache["tabs"].pop(next(iter(cache["tabs"])))
+            hit = cache["tabs"][key] = (host, tab)
+        if cache["spare"] is None and not capturing:
+            shape = (len(rows), 4)
+            cache["spare"] = (torch.empty(shape, dtype=torch.int64).pin_memory(), torch.empty(shape, dtype=torch.int64, device=dev))
+        return hit[1]
+
     @torch.no_grad()
     def step(self, closure=None):
         loss = None
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
-        for group in self.param_groups:
+        for gi, group in enumerate(self.param_groups):
             rows, keep = [], []
             for p in group["params"]:
                 if p.grad is None:
@@ -89,13 +138,13 @@ class SGD(torch.optim.Optimizer):
                 rows.append((p.data_ptr(), g.data_ptr(), m.data_ptr(), p.numel()))
                 keep.append(g)
             dev = group["params"][0].device
-            lr = torch.full((1,), float(group["lr"]), dtype=torch.float32, device=dev)
+            lr = self._lr_tensor(gi, group, dev)
             if self._factored:
                 with torch.cuda.device(dev):
                     self._step_factored(group, lr)
             if not rows:
                 continue
-            tab = torch.from_numpy(np.asarray(rows, dtype=np.int64)).to(dev)
+            tab = self._table(gi, rows, dev)
             ct, co = self._chunks([r[3] for r in rows], dev)
             with torch.cuda.device(dev):
                 call("icl_sgd_multi", P(tab), P(ct), P(co), c_int(ct.numel()), P(lr), c_f(group["momentum"]), c_f(group["weight_decay"]),

@@ -74,8 +74,10 @@ int icl_maxpool3d_bwd(const float* dout, const unsigned char* idx, float* dx, in
 int icl_upsample2x_fwd(const float* x, float* out, void* pk, int write_lo, int B, int C, int d, int h, int w, void* stream);
 int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int B, int C, int d, int h, int w, void* stream);
 
-/* ---- nn.Dropout(p=0.3): networks/unet_3D_icl.py:67-68,110,116 (mask bytes, or Philox keyed by seed) ---- */
-int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, float p, long long total, void* stream);
+/* ---- nn.Dropout(p=0.3): networks/unet_3D_icl.py:67-68,110,116 (mask bytes, or Philox keyed by seed; seed_ptr = seed in device memory,
+        so that a captured CUDA graph can be re-seeded per replay) ---- */
+int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, const unsigned long long* seed_ptr, float p,
+                long long total, void* stream);
 
 /* ---- elementwise helpers for residual adds / DropPath row scaling: networks/unet_3D_icl.py:264-267 ---- */
 int icl_axpby(const float* x, float* y, float alpha, float beta, long long n, void* stream);
