@@ -42,7 +42,8 @@ def parse():
     ap.add_argument("--precision", default="parity", choices=["parity", "fast"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
-    ap.add_argument("--fused-optimizer", action="store_true", help="apply the mlp2 weight gradients as rank-R updates inside the optimizer")
+    ap.add_argument("--unfused-optimizer", action="store_true", help="materialise the mlp2 weight gradients (reference-style .grad) instead of "
+                    "applying them as rank-R updates inside the optimizer")
     ap.add_argument("--no-graph", action="store_true", help="eager step (one Python-enqueued launch per kernel) instead of CUDA-graph replay")
     ap.add_argument("--detail", default="", help="write the per-(kernel, shape) CUDA-event breakdown to this JSON file")
     return ap.parse_args()
@@ -183,8 +184,8 @@ def main_gpu(a):
     synth.load_synth(net, 1337)
     net.to(dev).train()
     # fused_factored: the 13 824^2 mlp2 weight gradients are applied as rank-32 updates inside the optimizer
-    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4, fused_factored=a.fused_optimizer)
-    dp = parallel.GradAverager(net, world, factored=not a.fused_optimizer) if world > 1 else None
+    opt = SGD(net.parameters(), lr=BASE_LR, momentum=0.9, weight_decay=1e-4, fused_factored=not a.unfused_optimizer)
+    dp = parallel.GradAverager(net, world, factored=a.unfused_optimizer) if world > 1 else None
     ce_loss, dice_loss = L.CrossEntropyLoss(), L.DiceLoss(K_CLASSES)
     aux_loss, pse_loss = L.AuxLoss3D(K_CLASSES), L.PseudoSoftLoss3D(K_CLASSES)
 
@@ -250,13 +251,14 @@ def main_gpu(a):
         return ms / n
 
     # ---- CUDA-graph replay of the whole step (single GPU; the eager step is host-bound)
-    use_graph = (not a.no_graph) and world == 1
+    use_graph = not a.no_graph
     eager_step = step
     if use_graph:
         from icl_b200.graph import GraphedStep
         for _ in range(2):
             eager_step(x_dev, y_dev)
         lc0 = _lib.launch_count()
+        # N > 1: the step's NCCL collectives (gradient all-reduce, factor all-gather) are captured with it
         graphed = GraphedStep(eager_step, (x_dev, y_dev), opt, warmup=1)
         # our kernel nodes in the captured graph = C-ABI launches issued by the (1 warm-up + 1 captured) step executions
         graph_launches_per_step = (_lib.launch_count() - lc0) // 2
