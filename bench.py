@@ -365,7 +365,13 @@ def main_gpu(a):
             line["cpu_baseline"] = cpu
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # destroy_process_group() hangs while a captured CUDA graph still holds NCCL work; the JSON line is out, so leave
+        # without the collective teardown
+        dist.barrier()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":
