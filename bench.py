@@ -346,20 +346,31 @@ def main_gpu(a):
             "conv_tensor_util": {"algorithmic_gflop_per_step": CONV_GFLOP_PER_STEP},
         }
         if prof:
+            # dominant kernel = largest share of the step's device time (CUDA events around every launch of our kernels in an
+            # eager pass of the same step, on the launching stream); achieved = algorithmic FLOPs or bytes / that time
             top = prof["kernels"][0]
             line["kernels"] = prof["kernels"][:12]
             conv_ms = sum(k["ms_per_step"] for k in prof["kernels"] if k["name"].startswith("icl_conv3d"))
             line["conv_tensor_util"].update({
                 "conv_kernel_ms_per_step": conv_ms,
                 "achieved_tflops": CONV_GFLOP_PER_STEP / conv_ms if conv_ms else None,
-                "frac_of_sustained_peak": (CONV_GFLOP_PER_STEP / conv_ms) / pk["tf_sus"] if conv_ms else None})
+                "frac_of_sustained_peak": (CONV_GFLOP_PER_STEP / conv_ms) / pk["tf_sus"] if conv_ms else None,
+                "mma_issue_frac_of_sustained_peak": ((3.0 if a.precision == "parity" else 1.0) * CONV_GFLOP_PER_STEP / conv_ms) / pk["tf_sus"]
+                if conv_ms else None})
             bound = "tensor" if top["name"].startswith("icl_conv3d") else "hbm"
             if bound == "tensor":
                 ach, peak, unit = top["gflop_per_launch"] / top["ms_per_launch"], pk["tf_sus"], "TFLOP/s"
             else:
                 ach, peak, unit = top["mbytes_per_launch"] / top["ms_per_launch"], pk["hbm"], "GB/s"
+            traffic = None
+            tpath = os.path.join(ROOT, "profiles", "traffic_r01.json")
+            if os.path.exists(tpath):
+                ent = json.load(open(tpath)).get(top["name"])
+                if ent:
+                    traffic = {"bytes_per_launch": ent["traffic_bytes"], "algorithmic_bytes": ent["algorithmic_bytes"], "shape": ent["shape"],
+                               "source": ent["source"]}
             line["roofline"] = {"kernel": top["name"], "bound": bound, "achieved": ach, "peak": peak, "unit": unit,
-                                "frac": ach / peak if peak else None, "traffic": None, "peak_source": pk["src"] + " (sustained)",
+                                "frac": ach / peak if peak else None, "traffic": traffic, "peak_source": pk["src"] + " (sustained)",
                                 "share_of_step": top["share"], "launches_per_step": top["launches_per_step"]}
         if cpu:
             line["cpu_baseline"] = cpu

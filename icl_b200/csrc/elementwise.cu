@@ -582,6 +582,95 @@ ICL_API int icl_dropout(const float* x, float* out, const unsigned char* mask, u
 }
 
 // ------------------------------------------------------------------------------------------
+// `final` 1x1x1 Conv3d(16 -> K) at full resolution (networks/unet_3D_icl.py:65,117) and its backward.  M = all voxels,
+// N = K <= 16, reduction = 16 channels: pure streaming (64 B in, 4K B out per voxel) — a tiled GEMM wastes > 90 % of
+// its tile on N = 2.  Backward reads g and x once and emits dx, dW and db together (K <= 4: dW / db live in registers).
+// ------------------------------------------------------------------------------------------
+#define HD_C 16
+__global__ void __launch_bounds__(256) head1x1_fwd_k(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                                                     float* __restrict__ out, long long rows, int K) {
+  __shared__ float ws[16 * HD_C + 16];
+  for (int i = threadIdx.x; i < K * HD_C; i += 256) ws[i] = w[i];
+  for (int i = threadIdx.x; i < K; i += 256) ws[16 * HD_C + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < rows; v += (long long)gridDim.x * 256) {
+    float xv[HD_C];
+    const float4* xp = reinterpret_cast<const float4*>(x + v * HD_C);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 t = xp[q]; xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w; }
+    for (int k = 0; k < K; ++k) {
+      float a = ws[16 * HD_C + k];
+#pragma unroll
+      for (int c = 0; c < HD_C; ++c) a = fmaf(xv[c], ws[k * HD_C + c], a);
+      out[v * K + k] = a;
+    }
+  }
+}
+ICL_API int icl_head1x1_fwd(const float* x, const float* w, const float* bias, float* out, long long rows, int C, int K, void* stream) {
+  ICL_REQUIRE(C == HD_C && K >= 1 && K <= 16, "head1x1_fwd: C=%d K=%d unsupported (C must be 16, K <= 16)", C, K);
+  head1x1_fwd_k<<<grid_for(rows, 256, 148 * 8), 256, 0, as_stream(stream)>>>(x, w, bias, out, rows, K);
+  ICL_LAUNCHED("head1x1_fwd");
+}
+template <int KT>
+__global__ void __launch_bounds__(256) head1x1_bwd_k(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                                                     float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows) {
+  __shared__ float ws[KT * HD_C];
+  __shared__ float red[8][KT * HD_C + KT];
+  for (int i = threadIdx.x; i < KT * HD_C; i += 256) ws[i] = w[i];
+  __syncthreads();
+  float aw[KT][HD_C], ab[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    ab[k] = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) aw[k][c] = 0.f;
+  }
+  for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < rows; v += (long long)gridDim.x * 256) {
+    float xv[HD_C], gv[KT], o[HD_C];
+    const float4* xp = reinterpret_cast<const float4*>(x + v * HD_C);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { const float4 t = xp[q]; xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w; }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) gv[k] = g[v * KT + k];
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k) {
+      ab[k] += gv[k];
+#pragma unroll
+      for (int c = 0; c < HD_C; ++c) { o[c] = fmaf(gv[k], ws[k * HD_C + c], o[c]); aw[k][c] = fmaf(gv[k], xv[c], aw[k][c]); }
+    }
+    float4* dp = reinterpret_cast<float4*>(dx + v * HD_C);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dp[q] = make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) { const float t = warp_sum(aw[k][c]); if (lane == 0) red[wid][k * HD_C + c] = t; }
+    const float t = warp_sum(ab[k]);
+    if (lane == 0) red[wid][KT * HD_C + k] = t;
+  }
+  __syncthreads();
+  if (threadIdx.x < KT * HD_C + KT) {
+    float t = 0.f;
+    for (int i = 0; i < 8; ++i) t += red[i][threadIdx.x];
+    if (threadIdx.x < KT * HD_C) atomicAdd(dw + threadIdx.x, t);
+    else atomicAdd(db + (threadIdx.x - KT * HD_C), t);
+  }
+}
+ICL_API int icl_head1x1_bwd(const float* g, const float* x, const float* w, float* dx, float* dw /* zeroed [K][16] */, float* db /* zeroed [K] */,
+                            long long rows, int C, int K, void* stream) {
+  ICL_REQUIRE(C == HD_C && (K == 1 || K == 2 || K == 4), "head1x1_bwd: C=%d K=%d unsupported (C = 16, K in {1,2,4})", C, K);
+  const int grid = grid_for(rows, 256, 148 * 4);
+  if (K == 1) head1x1_bwd_k<1><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);
+  else if (K == 2) head1x1_bwd_k<2><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);
+  else head1x1_bwd_k<4><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);
+  ICL_LAUNCHED("head1x1_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
 // small utilities:  y = alpha*x + beta*y ;  rows scaled by a per-row factor (DropPath)
 // ------------------------------------------------------------------------------------------
 __global__ void axpby_k(const float* __restrict__ x, float* __restrict__ y, float alpha, float beta, long long n) {

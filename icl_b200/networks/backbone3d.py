@@ -167,7 +167,11 @@ class Backbone3DFn(torch.autograd.Function):
         rows = B * D * H * W
         final = torch.empty((B, D, H, W, K), dtype=torch.float32, device=x_.device)
         wf2 = wf.reshape(K, -1)
-        ops.sgemm(rows, K, wf2.shape[1], up1d, wf2.shape[1], 1, wf2, 1, wf2.shape[1], final, K, 1, bias=bf, bias_mode=1)
+        if wf2.shape[1] == 16 and K <= 16:
+            ops.call("icl_head1x1_fwd", ops.P(up1d), ops.P(wf2), ops.P(bf), ops.P(final), ops.c_ll(rows), ops.c_int(16), ops.c_int(K),
+                     mbytes=4e-6 * rows * (16 + K))
+        else:
+            ops.sgemm(rows, K, wf2.shape[1], up1d, wf2.shape[1], 1, wf2, 1, wf2.shape[1], final, K, 1, bias=bf, bias_mode=1)
         rec["up1d"] = up1d
         ctx.rec, ctx.blk, ctx.wf, ctx.drop_cfg = rec, blk, wf2, drop_cfg
         ctx.needs_x = x.requires_grad
@@ -199,11 +203,17 @@ class Backbone3DFn(torch.autograd.Function):
             B, D, H, W, K = gf.shape
             rows, C1 = B * D * H * W, wf2.shape[1]
             d_up1d = torch.empty((B, D, H, W, C1), dtype=torch.float32, device=gf.device)
-            ops.sgemm(rows, C1, K, gf, K, 1, wf2, C1, 1, d_up1d, C1, 1)
-            dwf = torch.empty((K, C1), dtype=torch.float32, device=gf.device)
-            ops.sgemm(K, C1, rows, gf, 1, K, rec["up1d"], C1, 1, dwf, C1, 1)
-            dbf = torch.empty((K,), dtype=torch.float32, device=gf.device)
-            ops.call("icl_colsum", ops.P(gf), ops.P(dbf), ops.c_ll(rows), ops.c_int(K), ops.c_int(0), tag="%dx%d" % (rows, K))
+            if C1 == 16 and K in (1, 2, 4):
+                dwf = torch.zeros((K, C1), dtype=torch.float32, device=gf.device)
+                dbf = torch.zeros((K,), dtype=torch.float32, device=gf.device)
+                ops.call("icl_head1x1_bwd", ops.P(gf), ops.P(rec["up1d"]), ops.P(wf2), ops.P(d_up1d), ops.P(dwf), ops.P(dbf), ops.c_ll(rows),
+                         ops.c_int(16), ops.c_int(K), mbytes=4e-6 * rows * (32 + K))
+            else:
+                ops.sgemm(rows, C1, K, gf, K, 1, wf2, C1, 1, d_up1d, C1, 1)
+                dwf = torch.empty((K, C1), dtype=torch.float32, device=gf.device)
+                ops.sgemm(K, C1, rows, gf, 1, K, rec["up1d"], C1, 1, dwf, C1, 1)
+                dbf = torch.empty((K,), dtype=torch.float32, device=gf.device)
+                ops.call("icl_colsum", ops.P(gf), ops.P(dbf), ops.c_ll(rows), ops.c_int(K), ops.c_int(0), tag="%dx%d" % (rows, K))
             grads["final"] = [dwf.reshape(K, C1, 1, 1, 1), dbf]
             if drop_cfg is not None:
                 d_up1 = ops.dropout(d_up1d, drop_cfg[0], drop_cfg[2], drop_cfg[4])

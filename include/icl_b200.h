@@ -79,6 +79,10 @@ int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, int accu
 int icl_dropout(const float* x, float* out, const unsigned char* mask, unsigned long long seed, const unsigned long long* seed_ptr, float p,
                 long long total, void* stream);
 
+/* ---- `final` 1x1x1 Conv3d(16 -> K) over all voxels and its fused backward (dx, dW, db in one pass): networks/unet_3D_icl.py:65,117 ---- */
+int icl_head1x1_fwd(const float* x, const float* w, const float* bias, float* out, long long rows, int C, int K, void* stream);
+int icl_head1x1_bwd(const float* g, const float* x, const float* w, float* dx, float* dw, float* db, long long rows, int C, int K, void* stream);
+
 /* ---- elementwise helpers for residual adds / DropPath row scaling: networks/unet_3D_icl.py:264-267 ---- */
 int icl_axpby(const float* x, float* y, float alpha, float beta, long long n, void* stream);
 int icl_row_combine(const float* a, const float* sa, const float* b, const float* sb, float* out, long long rows, long long cols, void* stream);

@@ -514,6 +514,31 @@ def test_losses_small(K):
     assert_close(l3.grad.cpu(), l2.grad, 1e-4, "weighted dice grad")
 
 
+@pytest.mark.parametrize("K", [2, 4, 16])
+def test_head1x1_fwd_bwd(K):
+    """`final` 1x1x1 conv (16 -> K) streaming kernels vs F.conv3d and its autograd."""
+    ops = _ops()
+    rows = 70003
+    x = torch.randn(rows, 16, generator=g(1), requires_grad=True)
+    w = (torch.randn(K, 16, generator=g(2)) * 0.3).requires_grad_(True)
+    b = torch.randn(K, generator=g(3)).requires_grad_(True)
+    gy = torch.randn(rows, K, generator=g(4))
+    ref = F.linear(x, w, b)
+    ref.backward(gy)
+    out = torch.empty(rows, K, device="cuda")
+    ops.call("icl_head1x1_fwd", ops.P(x.detach().cuda()), ops.P(w.detach().cuda()), ops.P(b.detach().cuda()), ops.P(out), ops.c_ll(rows),
+             ops.c_int(16), ops.c_int(K))
+    assert_close(out.cpu(), ref.detach(), 1e-6, "head fwd")
+    if K <= 4:
+        dx = torch.empty(rows, 16, device="cuda")
+        dw, db = torch.zeros(K, 16, device="cuda"), torch.zeros(K, device="cuda")
+        ops.call("icl_head1x1_bwd", ops.P(gy.cuda()), ops.P(x.detach().cuda()), ops.P(w.detach().cuda()), ops.P(dx), ops.P(dw), ops.P(db),
+                 ops.c_ll(rows), ops.c_int(16), ops.c_int(K))
+        assert_close(dx.cpu(), x.grad, 1e-6, "head dx")
+        assert_close(dw.cpu(), w.grad, 2e-5, "head dw")
+        assert_close(db.cpu(), b.grad, 2e-5, "head db")
+
+
 def test_sgd_multi_matches_torch():
     from icl_b200.optim import SGD
     shapes = [(5,), (33, 7), (70000,), (16, 16, 3, 3, 3), (1,)]
