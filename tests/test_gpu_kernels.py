@@ -526,14 +526,13 @@ def test_head1x1_fwd_bwd(K):
     ref = F.linear(x, w, b)
     ref.backward(gy)
     out = torch.empty(rows, K, device="cuda")
-    ops.call("icl_head1x1_fwd", ops.P(x.detach().cuda()), ops.P(w.detach().cuda()), ops.P(b.detach().cuda()), ops.P(out), ops.c_ll(rows),
-             ops.c_int(16), ops.c_int(K))
+    xc, wc, bc, gc = x.detach().cuda(), w.detach().cuda(), b.detach().cuda(), gy.cuda()  # keep the device buffers alive
+    ops.call("icl_head1x1_fwd", ops.P(xc), ops.P(wc), ops.P(bc), ops.P(out), ops.c_ll(rows), ops.c_int(16), ops.c_int(K))
     assert_close(out.cpu(), ref.detach(), 1e-6, "head fwd")
     if K <= 4:
         dx = torch.empty(rows, 16, device="cuda")
         dw, db = torch.zeros(K, 16, device="cuda"), torch.zeros(K, device="cuda")
-        ops.call("icl_head1x1_bwd", ops.P(gy.cuda()), ops.P(x.detach().cuda()), ops.P(w.detach().cuda()), ops.P(dx), ops.P(dw), ops.P(db),
-                 ops.c_ll(rows), ops.c_int(16), ops.c_int(K))
+        ops.call("icl_head1x1_bwd", ops.P(gc), ops.P(xc), ops.P(wc), ops.P(dx), ops.P(dw), ops.P(db), ops.c_ll(rows), ops.c_int(16), ops.c_int(K))
         assert_close(dx.cpu(), x.grad, 1e-6, "head dx")
         assert_close(dw.cpu(), w.grad, 2e-5, "head dw")
         assert_close(db.cpu(), b.grad, 2e-5, "head db")
