@@ -189,26 +189,24 @@ __global__ void __launch_bounds__(256) trilinear_adjoint_k(const float* __restri
     const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
     const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
     const float* src = dfine + (long long)bk * g.Z * g.Y * g.X;
-    // separable weights, no per-voxel index division: lanes own x positions (contiguous loads), the warps of the group
-    // split z, y is walked serially; 1-D weights are evaluated once per lane (x) / per row (y) / per plane (z).
-    const int glane = gt & 31, gwarp = gt >> 5, gwarps = G >> 5;
+    // separable weights: a thread owns (y, x) positions of the footprint (one index division per position, not per voxel),
+    // keeps wy * wx in a register and walks z; consecutive threads read consecutive x.
     auto w1d = [](int j, float sc, int n, int c) {
       int i0, i1; float l1;
       lin_src(j, sc, n, i0, i1, l1);
       return (i0 == c ? 1.f - l1 : 0.f) + (i1 == c ? l1 : 0.f);
     };
-    const int xa = x0 + glane, xb = xa + 32;  // nx <= 2 * scale + 2 <= 64
-    const float wxa = xa <= x1 ? w1d(xa, g.sx, g.rx, cx) : 0.f, wxb = xb <= x1 ? w1d(xb, g.sx, g.rx, cx) : 0.f;
-    for (int z = z0 + gwarp; z <= z1; z += gwarps) {
-      const float wz = w1d(z, g.sz, g.rz, cz);
-      if (wz == 0.f) continue;
-      for (int y = y0; y <= y1; ++y) {
-        const float wzy = wz * w1d(y, g.sy, g.ry, cy);
-        if (wzy == 0.f) continue;
-        const float* row = src + ((long long)z * g.Y + y) * g.X;
-        if (wxa != 0.f) acc += wzy * wxa * row[xa];
-        if (wxb != 0.f) acc += wzy * wxb * row[xb];
+    for (int pr = gt; pr < ny * nx; pr += G) {
+      const int yy = pr / nx, xx = pr - yy * nx;
+      const float wyx = w1d(y0 + yy, g.sy, g.ry, cy) * w1d(x0 + xx, g.sx, g.rx, cx);
+      if (wyx == 0.f) continue;
+      const float* col = src + (long long)(y0 + yy) * g.X + (x0 + xx);
+      float a = 0.f;
+      for (int z = z0; z <= z1; ++z) {
+        const float wz = w1d(z, g.sz, g.rz, cz);
+        if (wz != 0.f) a += wz * col[(long long)z * g.Y * g.X];
       }
+      acc += wyx * a;
     }
     (void)nz; (void)ny; (void)nx;
   }

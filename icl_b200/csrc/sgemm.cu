@@ -283,6 +283,15 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
   // combined with atomics into y (zeroed by the host) and bias / activation run in skinny_bias_act_k afterwards.
   const int kbeg = blockIdx.y * k_per, kend = min(K, kbeg + k_per);
   for (int k0 = kbeg; k0 < kend; k0 += SK_KC) {
+    // the weight stream does not depend on the staged activations: issue the whole chunk's loads (16 x 128-bit per lane,
+    // 16 KB per warp in flight) BEFORE the activation staging and the barrier, so HBM latency overlaps both
+    float4 wv[SK_KC / 32][2];
+#pragma unroll
+    for (int u = 0; u < SK_KC / 32; ++u) {
+      const int k = k0 + u * 32 + 8 * t;
+      wv[u][0] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      wv[u][1] = (k + 4 < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < MT * 16 * (SK_KC / 4); i += 128) {
       const int m = i / (SK_KC / 4), kq = (i % (SK_KC / 4)) * 4;
@@ -296,36 +305,26 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
       *reinterpret_cast<uint2*>(&xl[m * SK_LD + kq + 2]) = make_uint2(l.z, l.w);
     }
     __syncthreads();
-#pragma unroll 1
-    for (int j0 = 0; j0 < SK_KC / 32; j0 += 4) {
-      float4 wv[4][2];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k = k0 + (j0 + u) * 32 + 8 * t;
-        wv[u][0] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
-        wv[u][1] = (k + 4 < kend) ? __ldg(reinterpret_cast<const float4*>(wrow + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+    for (int u = 0; u < SK_KC / 32; ++u) {
+      const float wf[8] = {wv[u][0].x, wv[u][0].y, wv[u][0].z, wv[u][0].w, wv[u][1].x, wv[u][1].y, wv[u][1].z, wv[u][1].w};
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const float wf[8] = {wv[u][0].x, wv[u][0].y, wv[u][0].z, wv[u][0].w, wv[u][1].x, wv[u][1].y, wv[u][1].z, wv[u][1].w};
+      for (int sidx = 0; sidx < 4; ++sidx) {
+        // MMA k-slot t   <- weight/activation column 32*u + 8t + 2*sidx
+        // MMA k-slot t+4 <- column 32*u + 8t + 2*sidx + 1
+        uint32_t b0h, b0l, b1h, b1l;
+        split_tf32(wf[2 * sidx], b0h, b0l);
+        split_tf32(wf[2 * sidx + 1], b1h, b1l);
+        const int col = u * 32 + 8 * t + 2 * sidx;
 #pragma unroll
-        for (int sidx = 0; sidx < 4; ++sidx) {
-          // MMA k-slot t   <- weight/activation column 32*(j0+u) + 8t + 2*sidx
-          // MMA k-slot t+4 <- column 32*(j0+u) + 8t + 2*sidx + 1
-          uint32_t b0h, b0l, b1h, b1l;
-          split_tf32(wf[2 * sidx], b0h, b0l);
-          split_tf32(wf[2 * sidx + 1], b1h, b1l);
-          const int col = (j0 + u) * 32 + 8 * t + 2 * sidx;
-#pragma unroll
-          for (int mt = 0; mt < MT; ++mt) {
-            const uint2 ah0 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g) * SK_LD + col]);
-            const uint2 ah1 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g + 8) * SK_LD + col]);
-            const uint2 al0 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g) * SK_LD + col]);
-            const uint2 al1 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g + 8) * SK_LD + col]);
-            mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0h, b1h);
-            mma_tf32(acc[mt], al0.x, al1.x, al0.y, al1.y, b0h, b1h);
-            mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0l, b1l);
-          }
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint2 ah0 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g) * SK_LD + col]);
+          const uint2 ah1 = *reinterpret_cast<const uint2*>(&xh[(mt * 16 + g + 8) * SK_LD + col]);
+          const uint2 al0 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g) * SK_LD + col]);
+          const uint2 al1 = *reinterpret_cast<const uint2*>(&xl[(mt * 16 + g + 8) * SK_LD + col]);
+          mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0h, b1h);
+          mma_tf32(acc[mt], al0.x, al1.x, al0.y, al1.y, b0h, b1h);
+          mma_tf32(acc[mt], ah0.x, ah1.x, ah0.y, ah1.y, b0l, b1l);
         }
       }
     }
