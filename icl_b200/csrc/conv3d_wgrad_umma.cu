@@ -180,30 +180,34 @@ conv3d_wgrad_umma_k(const __grid_constant__ CUtensorMap mapX, const __grid_const
 }
 
 // dW[co][ci_off + ci][kd][kh][kw] (+)= sum over splits and over the two (p, q) pairs with p - q = kd.
-__global__ void wgrad_reduce_k(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int Cin_total, int ci_off,
-                               int n_co_tiles, int splits, int accumulate) {
-  const long long total = (long long)Cout * Cin * 27;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    // thread order: co fastest (contiguous partial columns), then ci, then tap
-    long long r = i;
-    const int co = (int)(r % Cout); r /= Cout;
-    const int ci = (int)(r % Cin);
-    const int tap = (int)(r / Cin);
-    const int kd = tap / 9, t9 = tap % 9;
-    const int ob = (ci / 16) * n_co_tiles + co / 16;
-    const int c = (ci % 16) / 8, e = ci % 8, c2 = (co % 16) / 8, e2 = co % 8;
+// One CTA per (output block, in-plane tap): the 64 x 32 partial tiles of all splits are summed with coalesced float4 reads
+// in a fixed order (deterministic), staged in shared memory, then the 16 x 16 x 3 weights of this tap are gathered from it.
+__global__ void __launch_bounds__(256) wgrad_reduce_k(const float* __restrict__ partial, float* __restrict__ dw, int Cout, int Cin, int Cin_total,
+                                                      int ci_off, int n_co_tiles, int splits, int accumulate) {
+  __shared__ __align__(16) float tile[WG_M * WG_N];
+  const int ob = blockIdx.x / WG_TAPS, t9 = blockIdx.x % WG_TAPS;
+  float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+  const float4* base = reinterpret_cast<const float4*>(partial + ((long long)ob * splits * WG_TAPS + t9) * (WG_M * WG_N)) + threadIdx.x;
+  const long long sp_stride = (long long)WG_TAPS * (WG_M * WG_N) / 4;
+  for (int sp = 0; sp < splits; ++sp) {
+    const float4 v0 = base[sp * sp_stride], v1 = base[sp * sp_stride + 256];
+    a0.x += v0.x; a0.y += v0.y; a0.z += v0.z; a0.w += v0.w;
+    a1.x += v1.x; a1.y += v1.y; a1.z += v1.z; a1.w += v1.w;
+  }
+  reinterpret_cast<float4*>(tile)[threadIdx.x] = a0;
+  reinterpret_cast<float4*>(tile)[threadIdx.x + 256] = a1;
+  __syncthreads();
+  const int ci_tile = ob / n_co_tiles, co_tile = ob % n_co_tiles;
+  for (int i = threadIdx.x; i < 16 * 16 * 3; i += 256) {
+    const int co = i % 16, ci = (i / 16) % 16, kd = i / 256;
+    const int c = ci / 8, e = ci % 8, c2 = co / 8, e2 = co % 8;
     float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) {
-      const float* base = partial + ((long long)(ob * splits + sp) * WG_TAPS + t9) * (WG_M * WG_N);
 #pragma unroll
-      for (int q = 0; q < WG_PQ; ++q) {
-        const int m = (c * WG_PX + q + kd) * 8 + e, n = (c2 * WG_PQ + q) * 8 + e2;
-        s += base[m * WG_N + n];
-      }
-    }
-    float* d = dw + ((long long)co * Cin_total + ci_off + ci) * 27 + tap;
+    for (int q = 0; q < WG_PQ; ++q) s += tile[((c * WG_PX + q + kd) * 8 + e) * WG_N + (c2 * WG_PQ + q) * 8 + e2];
+    float* d = dw + ((long long)(co_tile * 16 + co) * Cin_total + ci_off + ci_tile * 16 + ci) * 27 + kd * 9 + t9;
     *d = accumulate ? *d + s : s;
   }
+  (void)Cout; (void)Cin;
 }
 
 static int make_wg_map(CUtensorMap* map, const void* pk, int P, int B, int C, int D, int H, int W, int box_w, int box_h, int box_d) {
@@ -259,7 +263,6 @@ ICL_API int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, 
   }
   conv3d_wgrad_umma_k<<<(unsigned)(blocks * p.splits), 192, smem, as_stream(stream)>>>(mx, my, p);
   icl_count_launch(1);
-  const long long total = (long long)Cout * Cin * 27;
-  wgrad_reduce_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(workspace, dw, Cout, Cin, Cin_total, ci_off, p.n_co_tiles, p.splits, accumulate);
+  wgrad_reduce_k<<<(unsigned)(blocks * WG_TAPS), 256, 0, as_stream(stream)>>>(workspace, dw, Cout, Cin, Cin_total, ci_off, p.n_co_tiles, p.splits, accumulate);
   ICL_LAUNCHED("conv3d_wgrad_umma");
 }

@@ -170,6 +170,7 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
       for (int j = 0; j < 4; ++j) { sg[j] += __shfl_xor_sync(0xffffffffu, sg[j], o); sgy[j] += __shfl_xor_sync(0xffffffffu, sgy[j], o); }
     }
     if ((int)(threadIdx.x & 31) < P4 || P4 >= 32) {
+      // P4 <= 8 (C <= 32): the few surviving lanes of a warp hit distinct addresses, and the 8 warps collide at most 8-way
 #pragma unroll
       for (int j = 0; j < 4; ++j) { atomicAdd(&sm[c + j], (double)sg[j]); atomicAdd(&sm[C + c + j], (double)sgy[j]); }
     }
@@ -264,7 +265,7 @@ __global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, 
 ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red /* [B,C,2] zeroed */, float* dY,
                                   void* pk, int write_lo, float* dbias /* [C] zeroed, or null */, int B, int C, long long S, void* stream) {
   ICL_REQUIRE(C <= 1024, "instnorm_relu_bwd: C=%d > 1024", C);
-  int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 65535) / 65536);
+  int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 16383) / 16384);
   if (chunks < 1) chunks = 1;
   instnorm_relu_bwd_reduce_k<<<dim3(chunks, B), 256, 2 * C * sizeof(double), as_stream(stream)>>>(dA, y, mr, red, C, S, chunks);
   icl_count_launch(1);
@@ -364,8 +365,34 @@ __global__ void maxpool_bwd_k(const float* __restrict__ dout, const unsigned cha
     dx[i] = accumulate ? dx[i] + g : g;
   }
 }
+// C % 4 == 0: thread = one input voxel x 4 channels (index math once per voxel, 128-bit accesses)
+__global__ void __launch_bounds__(256) maxpool_bwd_v4_k(const float* __restrict__ dout, const unsigned char* __restrict__ idx,
+                                                        float* __restrict__ dx, int accumulate, int B, int C, int D, int H, int W) {
+  const int Do = D / 2, Ho = H / 2, Wo = W / 2, C4 = C >> 2;
+  const long long total = (long long)B * D * H * W * C4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C4) * 4;
+    long long v = i / C4;
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H); v /= H;
+    const int d = (int)(v % D);
+    const int b = (int)(v / D);
+    const long long o = ((((long long)b * Do + d / 2) * Ho + h / 2) * Wo + w / 2) * C + c;
+    const int p = ((d & 1) << 2) | ((h & 1) << 1) | (w & 1);
+    const uchar4 id = *reinterpret_cast<const uchar4*>(idx + o);
+    const float4 g = *reinterpret_cast<const float4*>(dout + o);
+    float4 r = make_float4(id.x == p ? g.x : 0.f, id.y == p ? g.y : 0.f, id.z == p ? g.z : 0.f, id.w == p ? g.w : 0.f);
+    float4* dst = reinterpret_cast<float4*>(dx + ((((long long)b * D + d) * H + h) * W + w) * C + c);
+    if (accumulate) { const float4 q = *dst; r.x += q.x; r.y += q.y; r.z += q.z; r.w += q.w; }
+    *dst = r;
+  }
+}
 ICL_API int icl_maxpool3d_bwd(const float* dout, const unsigned char* idx, float* dx, int accumulate, int B, int C, int D, int H, int W,
                               void* stream) {
+  if (C % 4 == 0) {
+    maxpool_bwd_v4_k<<<grid_for((long long)B * (C / 4) * D * H * W, 256), 256, 0, as_stream(stream)>>>(dout, idx, dx, accumulate, B, C, D, H, W);
+    ICL_LAUNCHED("maxpool3d_bwd");
+  }
   long long total = (long long)B * C * D * H * W;
   maxpool_bwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dout, idx, dx, accumulate, B, C, D, H, W);
   ICL_LAUNCHED("maxpool3d_bwd");

@@ -173,42 +173,44 @@ __device__ __forceinline__ void voxel_dlogits(const float* __restrict__ src, con
 __global__ void __launch_bounds__(256) trilinear_adjoint_k(const float* __restrict__ dfine, SrcGeom g, int K, float* __restrict__ dsrc, int G,
                                                            long long cells) {
   __shared__ float red[8];
+  __shared__ float wzs[8][72];  // per thread group: the 1-D z weights of its cell (footprint <= 2 * scale + 2 <= 66 planes)
   const int per_block = 256 / G;
   const long long cell = (long long)blockIdx.x * per_block + threadIdx.x / G;  // cell index includes the class: ((b*K + k)*rz + cz)...
-  const int gt = threadIdx.x % G;
+  const int gt = threadIdx.x % G, grp = threadIdx.x / G;
+  const bool live = cell < cells;
   float acc = 0.f;
   int bk = 0, cz = 0, cy = 0, cx = 0;
-  if (cell < cells) {
-    long long c = cell;
-    cx = (int)(c % g.rx); c /= g.rx;
-    cy = (int)(c % g.ry); c /= g.ry;
-    cz = (int)(c % g.rz); bk = (int)(c / g.rz);
-    const int fz = g.Z / g.rz, fy = g.Y / g.ry, fx = g.X / g.rx;  // integer scale factors (host-checked)
-    const int z0 = max(0, cz * fz - fz / 2 - 1), z1 = min(g.Z - 1, cz * fz + (3 * fz) / 2);
-    const int y0 = max(0, cy * fy - fy / 2 - 1), y1 = min(g.Y - 1, cy * fy + (3 * fy) / 2);
-    const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
-    const int nz = z1 - z0 + 1, ny = y1 - y0 + 1, nx = x1 - x0 + 1;
-    const float* src = dfine + (long long)bk * g.Z * g.Y * g.X;
+  auto w1d = [](int j, float sc, int n, int c) {
+    int i0, i1; float l1;
+    lin_src(j, sc, n, i0, i1, l1);
+    return (i0 == c ? 1.f - l1 : 0.f) + (i1 == c ? l1 : 0.f);
+  };
+  long long c = live ? cell : 0;
+  cx = (int)(c % g.rx); c /= g.rx;
+  cy = (int)(c % g.ry); c /= g.ry;
+  cz = (int)(c % g.rz); bk = (int)(c / g.rz);
+  const int fz = g.Z / g.rz, fy = g.Y / g.ry, fx = g.X / g.rx;  // integer scale factors (host-checked)
+  const int z0 = max(0, cz * fz - fz / 2 - 1), z1 = min(g.Z - 1, cz * fz + (3 * fz) / 2);
+  const int y0 = max(0, cy * fy - fy / 2 - 1), y1 = min(g.Y - 1, cy * fy + (3 * fy) / 2);
+  const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
+  const int nz = min(72, z1 - z0 + 1), ny = y1 - y0 + 1, nx = x1 - x0 + 1;
+  for (int i = gt; i < nz; i += G) wzs[grp][i] = w1d(z0 + i, g.sz, g.rz, cz);
+  __syncthreads();
+  if (live) {
     // separable weights: a thread owns (y, x) positions of the footprint (one index division per position, not per voxel),
-    // keeps wy * wx in a register and walks z; consecutive threads read consecutive x.
-    auto w1d = [](int j, float sc, int n, int c) {
-      int i0, i1; float l1;
-      lin_src(j, sc, n, i0, i1, l1);
-      return (i0 == c ? 1.f - l1 : 0.f) + (i1 == c ? l1 : 0.f);
-    };
+    // keeps wy * wx in a register and walks z with the tabulated z weights; consecutive threads read consecutive x.
+    const float* src = dfine + (long long)bk * g.Z * g.Y * g.X;
+    const long long zs = (long long)g.Y * g.X;
     for (int pr = gt; pr < ny * nx; pr += G) {
       const int yy = pr / nx, xx = pr - yy * nx;
       const float wyx = w1d(y0 + yy, g.sy, g.ry, cy) * w1d(x0 + xx, g.sx, g.rx, cx);
       if (wyx == 0.f) continue;
-      const float* col = src + (long long)(y0 + yy) * g.X + (x0 + xx);
+      const float* col = src + (long long)z0 * zs + (long long)(y0 + yy) * g.X + (x0 + xx);
       float a = 0.f;
-      for (int z = z0; z <= z1; ++z) {
-        const float wz = w1d(z, g.sz, g.rz, cz);
-        if (wz != 0.f) a += wz * col[(long long)z * g.Y * g.X];
-      }
+#pragma unroll 4
+      for (int i = 0; i < nz; ++i) a = fmaf(wzs[grp][i], col[i * zs], a);
       acc += wyx * a;
     }
-    (void)nz; (void)ny; (void)nx;
   }
   acc = warp_sum(acc);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
