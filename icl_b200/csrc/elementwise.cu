@@ -80,15 +80,20 @@ ICL_API int icl_instnorm_stats(const float* y, double* stats, int B, int C, long
 // InstanceNorm + ReLU apply.  a = relu((y - mean) * rstd); optional PK output.
 // grid: (chunks over S, B*C8); block 256.
 // ------------------------------------------------------------------------------------------
+// gamma / beta (optional, per channel) and slope generalise InstanceNorm+ReLU to BatchNorm2d(affine)+LeakyReLU: with the
+// images of a 2D batch stacked along D of ONE sample, per-(sample, channel) statistics are exactly BatchNorm's batch
+// statistics (networks/unet_icl.py:46-54).  a = act(gamma * yh + beta), act(v) = v > 0 ? v : slope * v.
 __global__ void instnorm_relu_fwd_k(const float* __restrict__ y, const float* __restrict__ mr, float* __restrict__ a,
-                                    __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, long long S) {
+                                    __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, long long S,
+                                    const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
   const int C8 = C >> 3;
   const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
-  float mean[8], rstd[8];
+  float mean[8], rstd[8], sh[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     mean[i] = mr[((long long)b * C + c8 * 8 + i) * 2];
-    rstd[i] = mr[((long long)b * C + c8 * 8 + i) * 2 + 1];
+    rstd[i] = mr[((long long)b * C + c8 * 8 + i) * 2 + 1] * (gamma ? gamma[c8 * 8 + i] : 1.f);
+    sh[i] = beta ? beta[c8 * 8 + i] : 0.f;
   }
   const long long plane = (long long)B * C8 * S * 8;
   __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
@@ -97,31 +102,37 @@ __global__ void instnorm_relu_fwd_k(const float* __restrict__ y, const float* __
     float v[8];
     unpack8(ld8(y + off), v);
 #pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = fmaxf((v[i] - mean[i]) * rstd[i], 0.f);
+    for (int i = 0; i < 8; ++i) { const float t = (v[i] - mean[i]) * rstd[i] + sh[i]; v[i] = t > 0.f ? t : slope * t; }
     if (a) st8(a + off, v);
     if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, v);
   }
 }
 __global__ void instnorm_relu_fwd_generic_k(const float* __restrict__ y, const float* __restrict__ mr, float* __restrict__ a,
-                                            int C, long long S, long long total) {
+                                            int C, long long S, long long total, const float* __restrict__ gamma,
+                                            const float* __restrict__ beta, float slope) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long b = i / (S * C);
     const float m = mr[(b * C + c) * 2], r = mr[(b * C + c) * 2 + 1];
-    a[i] = fmaxf((y[i] - m) * r, 0.f);
+    const float t = (y[i] - m) * r * (gamma ? gamma[c] : 1.f) + (beta ? beta[c] : 0.f);
+    a[i] = t > 0.f ? t : slope * t;
   }
+}
+ICL_API int icl_normact_fwd(const float* y, const float* mr, const float* gamma, const float* beta, float slope, float* a, void* pk, int write_lo,
+                            int B, int C, long long S, void* stream) {
+  if (C % 8 == 0) {
+    int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
+    instnorm_relu_fwd_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(y, mr, a, (__nv_bfloat16*)pk, write_lo, B, C, S, gamma, beta, slope);
+  } else {
+    ICL_REQUIRE(pk == nullptr && a != nullptr, "normact_fwd: PK output needs C %% 8 == 0 (C=%d)", C);
+    long long total = (long long)B * S * C;
+    instnorm_relu_fwd_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(y, mr, a, C, S, total, gamma, beta, slope);
+  }
+  ICL_LAUNCHED("normact_fwd");
 }
 ICL_API int icl_instnorm_relu_fwd(const float* y, const float* mr, float* a, void* pk, int write_lo, int B, int C, long long S,
                                   void* stream) {
-  if (C % 8 == 0) {
-    int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
-    instnorm_relu_fwd_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(y, mr, a, (__nv_bfloat16*)pk, write_lo, B, C, S);
-  } else {
-    ICL_REQUIRE(pk == nullptr && a != nullptr, "instnorm_relu_fwd: PK output needs C %% 8 == 0 (C=%d)", C);
-    long long total = (long long)B * S * C;
-    instnorm_relu_fwd_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(y, mr, a, C, S, total);
-  }
-  ICL_LAUNCHED("instnorm_relu_fwd");
+  return icl_normact_fwd(y, mr, nullptr, nullptr, 0.f, a, pk, write_lo, B, C, S, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -130,8 +141,12 @@ ICL_API int icl_instnorm_relu_fwd(const float* y, const float* mr, float* a, voi
 // Pass 1 reduces (sum g, sum g*yh) per (b,c); pass 2 applies and optionally emits dY as PK and
 // accumulates sum_S dY (the conv-bias gradient; mathematically ~0 for InstanceNorm).
 // ------------------------------------------------------------------------------------------
+// With affine / leaky activation:  pre = gamma * yh + beta,  g' = dA * act'(pre);  the two sums reduced here are
+// sum g' (= dbeta) and sum g' * yh (= dgamma);  dY = rstd * gamma * (g' - mean(g') - yh * mean(g' * yh)).
+__device__ __forceinline__ float act_grad(float yh, float gm, float bt, float slope) { return (gm * yh + bt) > 0.f ? 1.f : slope; }
 __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
-                                           double* __restrict__ red, int C, long long S, int chunks) {
+                                           double* __restrict__ red, int C, long long S, int chunks, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float slope) {
   // grid (chunks, B); thread t owns channel group: channels handled as c = t % C lanes when C <= blockDim
   // Generic mapping: each thread walks elements i = s*C + c with stride blockDim (C divides blockDim or not).
   extern __shared__ double sm[];  // [2][C]
@@ -146,9 +161,12 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
   // C % 4 == 0 and (4 * blockDim) % C == 0: every thread keeps a fixed group of 4 channels and streams float4s.
   if (C % 4 == 0 && (4 * blockDim.x) % C == 0) {
     const int c = (threadIdx.x * 4) % C;
-    float m[4], r[4], sg[4] = {0.f, 0.f, 0.f, 0.f}, sgy[4] = {0.f, 0.f, 0.f, 0.f};
+    float m[4], r[4], gm[4], bt[4], sg[4] = {0.f, 0.f, 0.f, 0.f}, sgy[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int j = 0; j < 4; ++j) { m[j] = mr[((long long)b * C + c + j) * 2]; r[j] = mr[((long long)b * C + c + j) * 2 + 1]; }
+    for (int j = 0; j < 4; ++j) {
+      m[j] = mr[((long long)b * C + c + j) * 2]; r[j] = mr[((long long)b * C + c + j) * 2 + 1];
+      gm[j] = gamma ? gamma[c + j] : 1.f; bt[j] = beta ? beta[c + j] : 0.f;
+    }
     const long long n4 = n >> 2;
     const float4* y4 = reinterpret_cast<const float4*>(yb);
     const float4* d4 = reinterpret_cast<const float4*>(dAb);
@@ -159,7 +177,7 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float yh = (ya[j] - m[j]) * r[j];
-        const float g = yh > 0.f ? da[j] : 0.f;
+        const float g = da[j] * act_grad(yh, gm[j], bt[j], slope);
         sg[j] += g; sgy[j] += g * yh;
       }
     }
@@ -177,10 +195,11 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
   } else if (blockDim.x % C == 0) {
     const int c = threadIdx.x % C;
     const float m = mr[((long long)b * C + c) * 2], r = mr[((long long)b * C + c) * 2 + 1];
+    const float gm = gamma ? gamma[c] : 1.f, bt = beta ? beta[c] : 0.f;
     float sg = 0.f, sgy = 0.f;
     for (long long i = threadIdx.x; i < n; i += blockDim.x) {
       const float yh = (yb[i] - m) * r;
-      const float g = yh > 0.f ? dAb[i] : 0.f;
+      const float g = dAb[i] * act_grad(yh, gm, bt, slope);
       sg += g; sgy += g * yh;
     }
     atomicAdd(&sm[c], (double)sg);
@@ -190,7 +209,7 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
       const int c = (int)(i % C);
       const float m = mr[((long long)b * C + c) * 2], r = mr[((long long)b * C + c) * 2 + 1];
       const float yh = (yb[i] - m) * r;
-      const float g = yh > 0.f ? dAb[i] : 0.f;
+      const float g = dAb[i] * act_grad(yh, gamma ? gamma[c] : 1.f, beta ? beta[c] : 0.f, slope);
       atomicAdd(&sm[c], (double)g);
       atomicAdd(&sm[C + c], (double)(g * yh));
     }
@@ -204,18 +223,20 @@ __global__ void instnorm_relu_bwd_reduce_k(const float* __restrict__ dA, const f
 
 __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
                                           const double* __restrict__ red, float* __restrict__ dY, __nv_bfloat16* __restrict__ pk,
-                                          int write_lo, int B, int C, long long S, float* __restrict__ dbias) {
+                                          int write_lo, int B, int C, long long S, float* __restrict__ dbias,
+                                          const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
   __shared__ float bsum[8][8];
   float bacc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   const int C8 = C >> 3;
   const int b = blockIdx.y / C8, c8 = blockIdx.y % C8;
-  float mean[8], rstd[8], mg[8], mgy[8];
+  float mean[8], rstd[8], mg[8], mgy[8], gm[8], bt[8];
   const float invS = 1.f / (float)S;
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const long long k = (long long)b * C + c8 * 8 + i;
     mean[i] = mr[k * 2]; rstd[i] = mr[k * 2 + 1];
     mg[i] = (float)(red[k * 2] / (double)S); mgy[i] = (float)(red[k * 2 + 1] / (double)S);
+    gm[i] = gamma ? gamma[c8 * 8 + i] : 1.f; bt[i] = beta ? beta[c8 * 8 + i] : 0.f;
   }
   (void)invS;
   const long long plane = (long long)B * C8 * S * 8;
@@ -228,8 +249,8 @@ __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const fl
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const float yh = (yv[i] - mean[i]) * rstd[i];
-      const float g = yh > 0.f ? gv[i] : 0.f;
-      o[i] = rstd[i] * (g - mg[i] - yh * mgy[i]);
+      const float g = gv[i] * act_grad(yh, gm[i], bt[i], slope);
+      o[i] = rstd[i] * gm[i] * (g - mg[i] - yh * mgy[i]);
       bacc[i] += o[i];
     }
     if (dY) st8(dY + off, o);
@@ -251,33 +272,40 @@ __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const fl
   }
 }
 __global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
-                                                  const double* __restrict__ red, float* __restrict__ dY, int C, long long S, long long total) {
+                                                  const double* __restrict__ red, float* __restrict__ dY, int C, long long S, long long total,
+                                                  const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i % C);
     const long long k = (i / (S * C)) * C + c;
     const float m = mr[k * 2], r = mr[k * 2 + 1];
     const float mg = (float)(red[k * 2] / (double)S), mgy = (float)(red[k * 2 + 1] / (double)S);
     const float yh = (y[i] - m) * r;
-    const float g = yh > 0.f ? dA[i] : 0.f;
-    dY[i] = r * (g - mg - yh * mgy);
+    const float gmc = gamma ? gamma[c] : 1.f;
+    const float g = dA[i] * act_grad(yh, gmc, beta ? beta[c] : 0.f, slope);
+    dY[i] = r * gmc * (g - mg - yh * mgy);
   }
 }
-ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red /* [B,C,2] zeroed */, float* dY,
-                                  void* pk, int write_lo, float* dbias /* [C] zeroed, or null */, int B, int C, long long S, void* stream) {
-  ICL_REQUIRE(C <= 1024, "instnorm_relu_bwd: C=%d > 1024", C);
+ICL_API int icl_normact_bwd(const float* dA, const float* y, const float* mr, const float* gamma, const float* beta, float slope,
+                            double* red /* [B,C,2] zeroed; out: sum g' (= dbeta), sum g' yh (= dgamma) */, float* dY, void* pk, int write_lo,
+                            float* dbias /* [C] zeroed, or null */, int B, int C, long long S, void* stream) {
+  ICL_REQUIRE(C <= 1024, "normact_bwd: C=%d > 1024", C);
   int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 16383) / 16384);
   if (chunks < 1) chunks = 1;
-  instnorm_relu_bwd_reduce_k<<<dim3(chunks, B), 256, 2 * C * sizeof(double), as_stream(stream)>>>(dA, y, mr, red, C, S, chunks);
+  instnorm_relu_bwd_reduce_k<<<dim3(chunks, B), 256, 2 * C * sizeof(double), as_stream(stream)>>>(dA, y, mr, red, C, S, chunks, gamma, beta, slope);
   icl_count_launch(1);
   if (C % 8 == 0) {
     int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
-    instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S, dbias);
+    instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S, dbias, gamma, beta, slope);
   } else {
     ICL_REQUIRE(pk == nullptr && dY != nullptr && dbias == nullptr, "instnorm_relu_bwd: PK / bias-gradient outputs need C %% 8 == 0 (C=%d)", C);
     long long total = (long long)B * S * C;
-    instnorm_relu_bwd_apply_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, C, S, total);
+    instnorm_relu_bwd_apply_generic_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, C, S, total, gamma, beta, slope);
   }
-  ICL_LAUNCHED("instnorm_relu_bwd");
+  ICL_LAUNCHED("normact_bwd");
+}
+ICL_API int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red, float* dY, void* pk, int write_lo, float* dbias,
+                                  int B, int C, long long S, void* stream) {
+  return icl_normact_bwd(dA, y, mr, nullptr, nullptr, 0.f, red, dY, pk, write_lo, dbias, B, C, S, stream);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -396,6 +424,150 @@ ICL_API int icl_maxpool3d_bwd(const float* dout, const unsigned char* idx, float
   long long total = (long long)B * C * D * H * W;
   maxpool_bwd_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dout, idx, dx, accumulate, B, C, D, H, W);
   ICL_LAUNCHED("maxpool3d_bwd");
+}
+
+// ------------------------------------------------------------------------------------------
+// 2D path (networks/unet_icl.py): a batch of images is ONE sample with the images stacked along D, F32CL [1][Bimg][H][W][C].
+// MaxPool2d(2) (unet_icl.py:66) pools H and W only; first maximum in (h, w) scan order wins ties; idx in 0..3.
+// ------------------------------------------------------------------------------------------
+__global__ void maxpool2d_fwd_k(const float* __restrict__ x, float* __restrict__ out, unsigned char* __restrict__ idx,
+                                __nv_bfloat16* __restrict__ pk, int write_lo, int N, int C, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long So = (long long)N * Ho * Wo;
+  const long long total = So * C;
+  const int C8 = (C % 8 == 0) ? C / 8 : 0;
+  const long long plane = (long long)C8 * So * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int wo = (int)(v % Wo); v /= Wo;
+    const int ho = (int)(v % Ho);
+    const int n = (int)(v / Ho);
+    float best = 0.f; int bi = 0;
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int h = 2 * ho + (p >> 1), w = 2 * wo + (p & 1);
+      const float val = x[(((long long)n * H + h) * W + w) * C + c];
+      if (p == 0 || val > best || val != val) { best = val; bi = p; }
+    }
+    if (out) out[i] = best;
+    idx[i] = (unsigned char)bi;
+    if (pk) {
+      const long long sidx = ((long long)n * Ho + ho) * Wo + wo;
+      __nv_bfloat16 hi, lo; split_bf16(best, hi, lo);
+      const long long o = ((long long)(c >> 3) * So + sidx) * 8 + (c & 7);
+      pk[o] = hi;
+      if (write_lo) pk[plane + o] = lo;
+    }
+  }
+}
+__global__ void maxpool2d_bwd_k(const float* __restrict__ dout, const unsigned char* __restrict__ idx, float* __restrict__ dx, int accumulate,
+                                int N, int C, int H, int W) {
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)N * H * W * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int w = (int)(v % W); v /= W;
+    const int h = (int)(v % H);
+    const int n = (int)(v / H);
+    const long long o = (((long long)n * Ho + h / 2) * Wo + w / 2) * C + c;
+    const int p = ((h & 1) << 1) | (w & 1);
+    const float g = (idx[o] == p) ? dout[o] : 0.f;
+    dx[i] = accumulate ? dx[i] + g : g;
+  }
+}
+ICL_API int icl_maxpool2d_fwd(const float* x, float* out, unsigned char* idx, void* pk, int write_lo, int N, int C, int H, int W, void* stream) {
+  ICL_REQUIRE(H % 2 == 0 && W % 2 == 0, "maxpool2d: odd spatial size %dx%d", H, W);
+  ICL_REQUIRE(pk == nullptr || C % 8 == 0, "maxpool2d: PK output needs C %% 8 == 0");
+  maxpool2d_fwd_k<<<grid_for((long long)N * C * (H / 2) * (W / 2), 256), 256, 0, as_stream(stream)>>>(x, out, idx, (__nv_bfloat16*)pk, write_lo, N, C,
+                                                                                                   H, W);
+  ICL_LAUNCHED("maxpool2d_fwd");
+}
+ICL_API int icl_maxpool2d_bwd(const float* dout, const unsigned char* idx, float* dx, int accumulate, int N, int C, int H, int W, void* stream) {
+  maxpool2d_bwd_k<<<grid_for((long long)N * C * H * W, 256), 256, 0, as_stream(stream)>>>(dout, idx, dx, accumulate, N, C, H, W);
+  ICL_LAUNCHED("maxpool2d_bwd");
+}
+
+// nn.Upsample(scale_factor=2, mode='bilinear', align_corners=True) (unet_icl.py:84-85): src = dst * (n - 1) / (2n - 1).
+__device__ __forceinline__ void up2ac_src(int j, int n, int& i0, int& i1, float& l1) {
+  const float s = (n > 1) ? (float)j * ((float)(n - 1) / (float)(2 * n - 1)) : 0.f;
+  i0 = (int)s;
+  i1 = min(i0 + 1, n - 1);
+  l1 = s - (float)i0;
+}
+__global__ void upsample2x_ac2d_fwd_k(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ pk, int write_lo,
+                                      int N, int C, int h, int w) {
+  const int H = 2 * h, W = 2 * w;
+  const long long S = (long long)N * H * W;
+  const long long total = S * C;
+  const int C8 = (C % 8 == 0) ? C / 8 : 0;
+  const long long plane = (long long)C8 * S * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int X = (int)(v % W); v /= W;
+    const int Y = (int)(v % H);
+    const int n = (int)(v / H);
+    int y0, y1, x0, x1; float ly, lx;
+    up2ac_src(Y, h, y0, y1, ly); up2ac_src(X, w, x0, x1, lx);
+    const float* xb = x + (long long)n * h * w * C + c;
+#define AT(yy, xx) xb[((long long)(yy) * w + (xx)) * C]
+    // same association order as ATen's upsample_bilinear2d: w-lerp inside h-lerp
+    const float r = (1.f - ly) * ((1.f - lx) * AT(y0, x0) + lx * AT(y0, x1)) + ly * ((1.f - lx) * AT(y1, x0) + lx * AT(y1, x1));
+#undef AT
+    if (out) out[i] = r;
+    if (pk) {
+      const long long sidx = ((long long)n * H + Y) * W + X;
+      __nv_bfloat16 hi, lo; split_bf16(r, hi, lo);
+      const long long o = ((long long)(c >> 3) * S + sidx) * 8 + (c & 7);
+      pk[o] = hi;
+      if (write_lo) pk[plane + o] = lo;
+    }
+  }
+}
+__device__ __forceinline__ float up2ac_wt(int j, int n, int i) {
+  if (j < 0 || j >= 2 * n) return 0.f;
+  int i0, i1; float l1;
+  up2ac_src(j, n, i0, i1, l1);
+  float wgt = 0.f;
+  if (i0 == i) wgt += 1.f - l1;
+  if (i1 == i) wgt += l1;
+  return wgt;
+}
+// adjoint in gather form: coarse pixel i collects from the fine pixels j with src(j) in (i - 1, i + 1), i.e. j in [2i - 2, 2i + 3]
+__global__ void upsample2x_ac2d_bwd_k(const float* __restrict__ dout, int Cd, int c_off, float* __restrict__ dx, int accumulate, int N, int C, int h,
+                                      int w) {
+  const int H = 2 * h, W = 2 * w;
+  const long long total = (long long)N * h * w * C;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    long long v = i / C;
+    const int x = (int)(v % w); v /= w;
+    const int y = (int)(v % h);
+    const int n = (int)(v / h);
+    float acc = 0.f;
+    for (int dy = -2; dy <= 3; ++dy) {
+      const int Y = 2 * y + dy; const float wy = up2ac_wt(Y, h, y);
+      if (wy == 0.f) continue;
+      for (int dxx = -2; dxx <= 3; ++dxx) {
+        const int X = 2 * x + dxx; const float wx = up2ac_wt(X, w, x);
+        if (wx == 0.f) continue;
+        acc += wy * wx * dout[(((long long)n * H + Y) * W + X) * Cd + c_off + c];
+      }
+    }
+    dx[i] = accumulate ? dx[i] + acc : acc;
+  }
+}
+ICL_API int icl_upsample2x_ac2d_fwd(const float* x, float* out, void* pk, int write_lo, int N, int C, int h, int w, void* stream) {
+  ICL_REQUIRE(pk == nullptr || C % 8 == 0, "upsample2x_ac2d: PK output needs C %% 8 == 0");
+  ICL_REQUIRE(pk != nullptr || out != nullptr, "upsample2x_ac2d: no output requested");
+  upsample2x_ac2d_fwd_k<<<grid_for((long long)N * C * 4 * h * w, 256), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, N, C, h, w);
+  ICL_LAUNCHED("upsample2x_ac2d_fwd");
+}
+ICL_API int icl_upsample2x_ac2d_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int N, int C, int h, int w, void* stream) {
+  upsample2x_ac2d_bwd_k<<<grid_for((long long)N * C * h * w, 256), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate, N, C, h, w);
+  ICL_LAUNCHED("upsample2x_ac2d_bwd");
 }
 
 // ------------------------------------------------------------------------------------------

@@ -326,7 +326,8 @@ static int make_geom(SrcGeom& g, int planar, int rz, int ry, int rx, int Z, int 
   g.planar = planar; g.rz = rz; g.ry = ry; g.rx = rx; g.Z = Z; g.Y = Y; g.X = X;
   g.sz = (float)rz / (float)Z; g.sy = (float)ry / (float)Y; g.sx = (float)rx / (float)X;
   const bool direct = rz == Z && ry == Y && rx == X;
-  if (!direct && (2 * rz > Z || 2 * ry > Y || 2 * rx > X)) {
+  // an axis is either untouched (r == full, e.g. the depth-1 axis of the 2D path) or at most half the loss grid
+  if (!direct && ((rz != Z && 2 * rz > Z) || (ry != Y && 2 * ry > Y) || (rx != X && 2 * rx > X))) {
     icl_set_error("class_stats: interpolated source must be at most half the loss grid (%d,%d,%d -> %d,%d,%d)", rz, ry, rx, Z, Y, X);
     return -1;
   }

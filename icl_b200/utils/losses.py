@@ -14,9 +14,12 @@ from ..ops import P, c_d, c_f, c_int, c_ll, call
 
 
 def _layout(src):
-    """Returns (tensor, planar flag): channels-last 5-D tensors are consumed in place, anything else as planar."""
+    """Returns (tensor, planar flag): channels-last 5-D tensors are consumed in place, anything else as planar.
+    4-D [B,K,H,W] inputs (the 2D path) are handled as depth-1 volumes."""
+    if src.dim() == 4:
+        src = src.unsqueeze(2)
     if src.dim() != 5:
-        raise RuntimeError("icl_b200 losses expect 5-D [B,K,D,H,W] inputs")
+        raise RuntimeError("icl_b200 losses expect [B,K,D,H,W] or [B,K,H,W] inputs")
     if src.dtype != torch.float32:
         src = src.float()
     if src.shape[1] > 1 and src.permute(0, 2, 3, 4, 1).is_contiguous():
@@ -33,7 +36,7 @@ class _ClassStatsFn(torch.autograd.Function):
         s, planar = _layout(src.detach())
         B, K = s.shape[0], s.shape[1]
         rz, ry, rx = s.shape[2:]
-        Z, Y, X = size
+        Z, Y, X = size if len(size) == 3 else (1,) + tuple(size)
         if K > 16:
             raise RuntimeError("icl_b200 losses support up to 16 classes (got %d)" % K)
         if labels is not None:
@@ -41,7 +44,7 @@ class _ClassStatsFn(torch.autograd.Function):
             if labels.numel() != B * Z * Y * X:
                 raise RuntimeError("labels shape %s does not match loss grid %s" % (tuple(labels.shape), (B, Z, Y, X)))
         if tgt is not None:
-            tgt = ops.to_ndhwc(tgt.detach())
+            tgt = ops.to_ndhwc(tgt.detach() if tgt.dim() == 5 else tgt.detach().unsqueeze(2))
         sums = torch.zeros((3 * K + 1,), dtype=torch.float64, device=s.device)
         out2 = torch.empty((2,), dtype=torch.float32, device=s.device)
         call("icl_class_stats_fwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
@@ -64,6 +67,8 @@ class _ClassStatsFn(torch.autograd.Function):
         gd = None if g_dice is None else g_dice.detach().float().contiguous()
         call("icl_class_stats_bwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
              P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(gc), P(gd), c_f(1.0), c_f(1.0), P(ds), P(ws))
+        if len(shape) == 4:
+            ds = ds.squeeze(2)
         return ds, None, None, None, None, None
 
 
@@ -140,6 +145,20 @@ class PseudoSoftLoss3D(nn.Module):
             d = soft_dice(fm, tgt, self.resize)
             tot = d if tot is None else tot + d
         return tot / len(feat_maps)
+
+
+class AuxLoss(AuxLoss3D):
+    """utils/losses.py:233-251 (2D): feature maps bilinearly resized (align_corners=False) to `resize`, CE + Dice(softmax=True)."""
+
+    def __init__(self, n_classes, resize=(224, 224)):
+        super().__init__(n_classes, tuple(resize))
+
+
+class PseudoSoftLoss(PseudoSoftLoss3D):
+    """utils/losses.py:273-285 (2D)."""
+
+    def __init__(self, n_classes=None, resize=(224, 224)):
+        super().__init__(n_classes, tuple(resize))
 
 
 class _SoftmaxMseFn(torch.autograd.Function):

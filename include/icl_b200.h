@@ -65,6 +65,20 @@ int icl_instnorm_relu_fwd(const float* y, const float* mr, float* a, void* pk, i
 int icl_instnorm_relu_bwd(const float* dA, const float* y, const float* mr, double* red, float* dY, void* pk, int write_lo, float* dbias,
                           int B, int C, long long S, void* stream);
 int icl_pack_pk(const float* x, void* pk, int write_lo, int B, int C, long long S, void* stream);
+/* generalisation used by the 2D path: optional per-channel affine (gamma, beta) and LeakyReLU slope.  With the images of a 2D
+   batch stacked along D of one sample, the per-(sample, channel) statistics are nn.BatchNorm2d's batch statistics, so this is
+   Conv2d -> BatchNorm2d -> LeakyReLU of ConvBlock (networks/unet_icl.py:46-54).  red returns (sum g' = dbeta, sum g' yh = dgamma). */
+int icl_normact_fwd(const float* y, const float* mr, const float* gamma, const float* beta, float slope, float* a, void* pk, int write_lo, int B,
+                    int C, long long S, void* stream);
+int icl_normact_bwd(const float* dA, const float* y, const float* mr, const float* gamma, const float* beta, float slope, double* red, float* dY,
+                    void* pk, int write_lo, float* dbias, int B, int C, long long S, void* stream);
+
+/* ---- 2D path: nn.MaxPool2d(2) (unet_icl.py:66) and nn.Upsample(scale_factor=2, bilinear, align_corners=True) (unet_icl.py:84-85) on
+        F32CL [1][N images][H][W][C] ---- */
+int icl_maxpool2d_fwd(const float* x, float* out, unsigned char* idx, void* pk, int write_lo, int N, int C, int H, int W, void* stream);
+int icl_maxpool2d_bwd(const float* dout, const unsigned char* idx, float* dx, int accumulate, int N, int C, int H, int W, void* stream);
+int icl_upsample2x_ac2d_fwd(const float* x, float* out, void* pk, int write_lo, int N, int C, int h, int w, void* stream);
+int icl_upsample2x_ac2d_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int N, int C, int h, int w, void* stream);
 
 /* ---- nn.MaxPool3d(2): networks/unet_3D_icl.py:41,45,49,53 (first max in scan order wins ties) ---- */
 int icl_maxpool3d_fwd(const float* x, float* out, unsigned char* idx, void* pk, int write_lo, int B, int C, int D, int H, int W, void* stream);

@@ -175,6 +175,126 @@ def gen_step(ns, K, name, weights):
           "none", len(none), "time %.1fs" % (time.time() - t0))
 
 
+MINI2D = dict(in_chans=(64, 32, 16), res=[4, 8, 16], heads=(4, 2, 1), K=3, B=2)
+
+
+def gen_unet2d(ns, name, K, size, seed, B):
+    """2D UNet (config 1 backbone): logits, CE + Dice(softmax=True), parameter gradients, BatchNorm running statistics."""
+    m = ns.UNet(in_chns=1, class_num=K)
+    synth.load_synth(m, seed)
+    m.train()
+    eval_dropout_only(m)
+    x = synth.synth_volume((B, 1, size, size), seed + 1)
+    y = synth.synth_labels((B, size, size), K, seed + 2)
+    logits = m(x)
+    loss = torch.nn.CrossEntropyLoss()(logits, y) + ns.losses.DiceLoss(K)(logits, y.unsqueeze(1), softmax=True)
+    loss.backward()
+    out = dict(meta=np.array([K, size, seed, B]), logits=logits.detach().numpy(), loss=np.float64(loss.item()))
+    for k, p in m.named_parameters():
+        sm, v = summarize(p.grad)
+        out["gsum/" + k] = sm
+        out["gval/" + k] = v
+    for k, v in m.state_dict().items():
+        if "running" in k:
+            out["stat/" + k] = v.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "loss", loss.item())
+
+
+def gen_icl_head2d(ns):
+    c = MINI2D
+    ic = ns.InherentConsistent2d(in_chans=c["in_chans"], depths=(2, 2, 2), patch_size=(2, 2), input_resolution=c["res"],
+                                 num_classes=c["K"], num_heads=c["heads"])
+    synth.load_synth(ic, 31)
+    ic.train()
+    eval_dropout_only(ic)
+    feats = [synth.synth_volume((c["B"], ch, r, r), 40 + i).requires_grad_(True) for i, (ch, r) in enumerate(zip(c["in_chans"], c["res"]))]
+    fm_l, q_l = ic(feats, None, "labeled")
+    fm_u, q_u = ic(feats, [q.detach() for q in q_l], "unlabeled")
+    loss = sum((f ** 2).mean() for f in fm_l) + sum((f ** 2).mean() for f in fm_u) + sum((q ** 2).mean() for q in q_l)
+    loss.backward()
+    out = dict(loss=np.float64(loss.item()))
+    for i in range(3):
+        out["fm_l%d" % i] = fm_l[i].detach().numpy()
+        out["fm_u%d" % i] = fm_u[i].detach().numpy()
+        out["q_l%d" % i] = q_l[i].detach().numpy()
+        out["dfeat%d" % i] = feats[i].grad.numpy()
+    none = []
+    for k, p in ic.named_parameters():
+        if p.grad is None:
+            none.append(k)
+        else:
+            out["g/" + k] = p.grad.numpy()
+    out["grad_none"] = np.array(none)
+    np.savez_compressed(os.path.join(GOLDEN, "icl_head2d_mini.npz"), **out)
+    print("icl_head2d_mini loss", loss.item(), "grad None:", len(none))
+
+
+def gen_losses2d(ns, K=4, S=64, B=3):
+    L = ns.losses
+    labels = synth.synth_labels((B, S, S), K, 51)
+    out_lab = synth.synth_volume((B, K, S, S), 52).requires_grad_(True)
+    out_unlab = synth.synth_volume((B, K, S, S), 53)
+    fms = [synth.synth_volume((B, K, r, r), 60 + i).mul_(2.0).requires_grad_(True) for i, r in enumerate((8, 16, 32))]
+    fms2 = [synth.synth_volume((B, K, r, r), 70 + i).mul_(2.0).requires_grad_(True) for i, r in enumerate((8, 16, 32))]
+    fms3 = [synth.synth_volume((B, K, r, r), 80 + i).mul_(2.0) for i, r in enumerate((8, 16, 32))]
+    ce = torch.nn.CrossEntropyLoss()(out_lab, labels)
+    dice = L.DiceLoss(K)(out_lab, labels.unsqueeze(1), softmax=True)
+    aux = L.AuxLoss(K, resize=[S, S])(fms, labels)
+    pse = L.PseudoSoftLoss(K, resize=[S, S])(fms2, out_unlab)
+    cons = L.softmax_mse_loss(fms2, fms3)
+    total = ce + dice + aux + pse + 50 * cons
+    total.backward()
+    out = dict(meta=np.array([K, S, B]), ce=ce.item(), dice=dice.item(), aux=aux.item(), pse=pse.item(), cons=cons.item(), total=total.item(),
+               dout=out_lab.grad.numpy())
+    for i in range(3):
+        out["daux%d" % i] = fms[i].grad.numpy()
+        out["dpse%d" % i] = fms2[i].grad.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "losses2d_k4.npz"), **out)
+    print("losses2d_k4", {k: out[k] for k in ("ce", "dice", "aux", "pse", "cons", "total")})
+
+
+def gen_step2d(ns):
+    """Config 1: UNet_icl(1, 4), batch 24 (12 labeled + 12 unlabeled) x 1x256x256, one full forward + 5 losses + backward."""
+    t0 = time.time()
+    K = 4
+    m = ns.UNet_icl(1, K)
+    synth.load_synth(m, 1337)
+    m.train()
+    eval_dropout_only(m)
+    x = synth.synth_volume((24, 1, 256, 256), 1338)
+    y = synth.synth_labels((24, 256, 256), K, 1339)
+    L = ns.losses
+    o = m(x[:12], x[12:])
+    ce = torch.nn.CrossEntropyLoss()(o[0], y[:12].long())
+    dice = L.DiceLoss(K)(o[0], y[:12].unsqueeze(1), softmax=True)
+    aux = L.AuxLoss(K, resize=[256, 256])(o[2], y[:12])
+    pse = L.PseudoSoftLoss(K, resize=[256, 256])(o[3], o[1])
+    cons = L.softmax_mse_loss(o[3], o[4])
+    total = ce + dice + aux + pse + 50 * cons
+    total.backward()
+    out = dict(K=np.int64(K), ce=ce.item(), dice=dice.item(), aux=aux.item(), pse=pse.item(), cons=cons.item(), total=total.item())
+    for nm, t in (("out_lab", o[0]), ("out_unlab", o[1])):
+        sm, v = summarize(t, 4096)
+        out[nm + "_sum"], out[nm + "_val"] = sm, v
+        out[nm + "_argmax_count"] = np.bincount(t.argmax(1).reshape(-1).numpy(), minlength=K)
+    for j, nm in ((2, "maps_lab"), (3, "maps_unlab"), (4, "maps_consis")):
+        for i in range(3):
+            sm, v = summarize(o[j][i].detach(), 4096)
+            out["%s%d_sum" % (nm, i)], out["%s%d_val" % (nm, i)] = sm, v
+    none = []
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            none.append(k)
+            continue
+        sm, v = summarize(p.grad)
+        out["gsum/" + k] = sm
+        out["gval/" + k] = v
+    out["grad_none"] = np.array(none)
+    np.savez_compressed(os.path.join(GOLDEN, "step_cfg1.npz"), **out)
+    print("step_cfg1 losses", {k: out[k] for k in ("ce", "dice", "aux", "pse", "cons", "total")}, "none", len(none), "time %.1fs" % (time.time() - t0))
+
+
 def gen_sliding(ns):
     tsc = ref_import.load_test_single_case()
     m = ns.unet_3D(feature_scale=4, n_classes=2, in_channels=1)
@@ -213,6 +333,10 @@ def main():
         "step_cfg2": lambda: gen_step(ns, 2, "step_cfg2", (1, 1, 1, 1, 10)),
         "step_cfg3": lambda: gen_step(ns, 16, "step_cfg3", (1, 1, 1, 0.1, 10)),
         "sliding": lambda: gen_sliding(ns),
+        "unet2d": lambda: gen_unet2d(ns, "unet2d_k4_64", 4, 64, 21, 4),
+        "icl_head2d": lambda: gen_icl_head2d(ns),
+        "losses2d": lambda: gen_losses2d(ns),
+        "step_cfg1": lambda: gen_step2d(ns),
     }
     for k, fn in jobs.items():
         if a.only is None or a.only == k:

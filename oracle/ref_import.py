@@ -42,6 +42,11 @@ def load():
     ns.Query_Attention = m.Query_Attention
     ns.SeparableConv3d = m.SeparableConv3d
     ns.MLP = m.MLP
+    m2 = importlib.import_module("networks.unet_icl")   # 2D path (config 1)
+    ns.UNet_icl = m2.UNet_icl
+    ns.Encoder2d, ns.Decoder2d = m2.Encoder, m2.Decoder
+    ns.InherentConsistent2d = m2.InherentConsistent
+    ns.UNet = importlib.import_module("networks.unet").UNet
     ns.net_utils = importlib.import_module("networks.utils")
     ns.losses = importlib.import_module("utils.losses")
     return ns
