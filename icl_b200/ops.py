@@ -11,7 +11,7 @@ import os
 import torch
 
 from . import _lib
-from .precision import planes
+from .precision import planes, tensor_cores
 
 c_int, c_ll, c_f, c_d, c_ull = ctypes.c_int, ctypes.c_longlong, ctypes.c_float, ctypes.c_double, ctypes.c_ulonglong
 P = _lib.ptr
@@ -52,7 +52,7 @@ def pk_ok(C):
 def umma_ok(cins, cout, with_stats=True):
     """Shapes the tcgen05 implicit-GEMM kernel takes; everything else runs the fp32 CUDA-core kernel.
     ICL_DISABLE_UMMA=1 is a debugging knob that routes every conv to the CUDA-core kernel."""
-    if os.environ.get("ICL_DISABLE_UMMA") == "1":
+    if os.environ.get("ICL_DISABLE_UMMA") == "1" or not tensor_cores():
         return False
     return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and (cout <= 256 or not with_stats)
 
@@ -151,7 +151,7 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
 
 
 def wgrad_umma_ok(cins, cout):
-    if os.environ.get("ICL_DISABLE_UMMA") == "1":
+    if os.environ.get("ICL_DISABLE_UMMA") == "1" or not tensor_cores():
         return False
     return all(c % 16 == 0 for c in cins) and cout % 16 == 0
 

@@ -22,38 +22,159 @@ def eval_dropout_only(model):
             m.eval()
 
 
-def test_conv_bn_leaky_block_vs_torch():
-    """Conv2d -> BatchNorm2d(train) -> LeakyReLU with two concatenated sources: output, input / parameter gradients, running stats."""
+# --- a note on gradient tolerances --------------------------------------------------------------------------------------
+# (Leaky)ReLU derivatives are discontinuous at 0.  Two correct implementations whose pre-activations differ by rounding
+# (~1e-7 fp32 re-association, ~4e-6 in the split-bf16 "parity" mode) disagree on the sign of the few elements with
+# |pre| below that, and EACH such flip changes a BatchNorm beta gradient by ~|dA|, i.e. ~1/sqrt(N*H*W) of its value.
+# Measured on the B=4, 64x64 UNet (tools/debug_unet2d.py, tools/flip_analysis2d.py; logs in profiles/r01n_*): 1-3 flips per layer -> 2e-3 (fp32 kernels) .. 2e-2 (parity)
+# relative difference in the parameter gradients, and it varies run to run because the forward statistics use atomics.
+# So the parity of the BACKWARD ARITHMETIC is established with the activation pattern held fixed (the "mask-matched"
+# tests below, tolerance 1e-3 and measured ~5e-6; MaxPool winners are a second discrete choice of the same kind and are
+# held fixed too), flips are counted and bounded separately, and the comparisons with the
+# reference's fixtures keep a flip-sized tolerance on gradients while logits / losses keep the 1e-3 north-star bound.
+GRAD_FLIP_TOL = 3e-2
+
+
+def _masked_leaky(pre, mask, slope=0.01):
+    return torch.where(mask, pre, slope * pre)
+
+
+@pytest.mark.parametrize("mode", ["parity", "fp32"])
+@pytest.mark.parametrize("shape", [(4, 16, 32, 32, 24, 16), (4, 16, 0, 16, 64, 64), (4, 64, 0, 64, 16, 16), (4, 128, 128, 128, 8, 8),
+                                   (2, 16, 16, 16, 128, 128), (4, 256, 0, 256, 4, 4)])
+def test_conv_bn_leaky_block_vs_torch(mode, shape):
+    """Conv2d -> BatchNorm2d(train) -> LeakyReLU with one or two concatenated sources against torch float64 evaluated with the
+    SAME activation pattern: output, input / parameter gradients, running stats; sign disagreements counted."""
+    import icl_b200
     import icl_b200.functional2d as F2
-    N, c0, c1, cout, H, W = 4, 16, 32, 32, 24, 16
-    x0 = torch.randn(N, c0, H, W, generator=g(1), requires_grad=True)
-    x1 = torch.randn(N, c1, H, W, generator=g(2), requires_grad=True)
-    conv = torch.nn.Conv2d(c0 + c1, cout, 3, padding=1)
-    bn = torch.nn.BatchNorm2d(cout)
-    with torch.no_grad():
-        bn.weight.copy_(torch.rand(cout, generator=g(3)) + 0.5)
-        bn.bias.copy_(torch.randn(cout, generator=g(4)) * 0.3)
-    dy = torch.randn(N, cout, H, W, generator=g(5))
-    ref = F.leaky_relu(bn(conv(torch.cat([x0, x1], 1))), 0.01)
-    ref.backward(dy)
+    N, c0, c1, cout, H, W = shape
+    dev = "cuda"
+    gg = lambda s_: torch.Generator(device=dev).manual_seed(s_)
+    x0 = torch.randn(N, c0, H, W, device=dev, generator=gg(1))
+    x1 = torch.randn(N, c1, H, W, device=dev, generator=gg(2)) if c1 else None
+    k = 1.0 / ((c0 + c1) * 9) ** 0.5
+    w = (torch.rand(cout, c0 + c1, 3, 3, device=dev, generator=gg(6)) * 2 - 1) * k
+    b = (torch.rand(cout, device=dev, generator=gg(7)) * 2 - 1) * k
+    gamma = torch.rand(cout, device=dev, generator=gg(3)) + 0.5
+    beta = torch.randn(cout, device=dev, generator=gg(4)) * 0.3
+    dy = torch.randn(N, cout, H, W, device=dev, generator=gg(5))
+    icl_b200.set_precision(mode)
+    try:
+        a0 = x0.clone().requires_grad_(True)
+        a1 = x1.clone().requires_grad_(True) if c1 else None
+        pw, pb, pg, pbt = (t.clone().requires_grad_(True) for t in (w, b, gamma, beta))
+        rm, rv = torch.zeros(cout, device=dev), torch.ones(cout, device=dev)
+        out = F2.Conv2dBnActFn.apply(a0, a1, pw, pb, pg, pbt, rm, rv, True, 0.1, 1e-5, 0.01)
+        out.backward(dy)
+    finally:
+        icl_b200.set_precision("parity")
+    r0 = x0.double().requires_grad_(True)
+    r1 = x1.double().requires_grad_(True) if c1 else None
+    rw, rb, rg, rbt = (t.double().requires_grad_(True) for t in (w, b, gamma, beta))
+    yr = F.conv2d(torch.cat([r0, r1], 1) if c1 else r0, rw, rb, padding=1)
+    pre = F.batch_norm(yr, None, None, rg, rbt, True)
+    mask = out.detach() > 0
+    flips = (pre.detach() > 0) != mask
+    assert int(flips.sum()) <= max(2, 1e-4 * mask.numel()), "activation signs differ in %d elements" % int(flips.sum())
+    if flips.any():
+        assert pre.detach()[flips].abs().max().item() < 1e-4
+    ref = _masked_leaky(pre, mask)
+    ref.backward(dy.double())
+    assert_close(out.detach().cpu(), ref.detach().cpu(), 2e-4, "block fwd")
+    assert_close(a0.grad.cpu(), r0.grad.cpu(), 1e-3, "dx0")
+    if c1:
+        assert_close(a1.grad.cpu(), r1.grad.cpu(), 1e-3, "dx1")
+    assert_close(pw.grad.cpu(), rw.grad.cpu(), 1e-3, "dw")
+    assert_close(pg.grad.cpu(), rg.grad.cpu(), 1e-3, "dgamma")
+    assert_close(pbt.grad.cpu(), rbt.grad.cpu(), 1e-3, "dbeta")
+    assert pb.grad.abs().max().item() <= 1e-4 * dy.abs().sum().item() / cout  # conv bias before BatchNorm: exact gradient is 0
+    S = N * H * W
+    mean = yr.detach().mean((0, 2, 3))
+    var = yr.detach().var((0, 2, 3), unbiased=True)
+    assert_close(rm.cpu(), (0.1 * mean).cpu(), 1e-4, "running_mean", abs_floor=1e-6)
+    assert_close(rv.cpu(), (0.9 + 0.1 * var).cpu(), 1e-4, "running_var")
+
+
+def _replica_unet_forward(ref, x, outs):
+    """The 2D U-Net written with plain torch ops on `ref`'s (float64) parameters.  The two discontinuous choices — the
+    LeakyReLU sign pattern and the MaxPool2d winner — are taken from `outs`, the conv_bn_act outputs recorded from the icl_b200
+    forward in call order.  Returns (logits, number of sign / winner disagreements, elements)."""
+    it = iter([o > 0 for o in outs])
+    cnt = [0, 0]
+
+    def pool(x, ours):
+        idx = F.max_pool2d(ours, 2, return_indices=True)[1]
+        cnt[0] += int((F.max_pool2d(x.detach(), 2, return_indices=True)[1] != idx).sum())
+        cnt[1] += idx.numel()
+        n, c, h, w = idx.shape
+        return x.flatten(2).gather(2, idx.flatten(2)).view(n, c, h, w)
+
+    def half(x, conv, bn):
+        pre = F.batch_norm(F.conv2d(x, conv.weight, conv.bias, padding=1), None, None, bn.weight, bn.bias, True)
+        m = next(it)
+        cnt[0] += int(((pre.detach() > 0) != m).sum())
+        cnt[1] += m.numel()
+        return _masked_leaky(pre, m)
+
+    def block(cb, x):
+        s = cb.conv_conv
+        return half(half(x, s[0], s[1]), s[4], s[5])
+
+    e, d = ref.encoder, ref.decoder
+    feats = [block(e.in_conv, x)]
+    for i, dn in enumerate((e.down1, e.down2, e.down3, e.down4)):
+        feats.append(block(dn.maxpool_conv[1], pool(feats[-1], outs[2 * i + 1])))
+    y = feats[4]
+    for up, skip in ((d.up1, feats[3]), (d.up2, feats[2]), (d.up3, feats[1]), (d.up4, feats[0])):
+        y1 = F.interpolate(F.conv2d(y, up.conv1x1.weight, up.conv1x1.bias), scale_factor=2, mode="bilinear", align_corners=True)
+        y = block(up.conv, torch.cat([skip, y1], 1))
+    return F.conv2d(y, d.out_conv.weight, d.out_conv.bias, padding=1), cnt[0], cnt[1]
+
+
+@pytest.mark.parametrize("mode,size,B", [("parity", 64, 4), ("parity", 128, 2), ("fp32", 64, 4)])
+def test_unet2d_grads_mask_matched(monkeypatch, mode, size, B):
+    """Whole 2D UNet forward + backward against a plain-torch float64 replica that uses the same parameters and the same
+    LeakyReLU sign pattern / MaxPool winners: every parameter gradient within 1e-3; disagreements of the two forwards on those
+    discrete choices <= 2e-5 of the elements."""
     import copy
-    conv_c, bn_c = copy.deepcopy(conv).cuda(), torch.nn.BatchNorm2d(cout).cuda()
-    with torch.no_grad():
-        bn_c.weight.copy_(bn.weight); bn_c.bias.copy_(bn.bias)
-    for p in list(conv_c.parameters()) + list(bn_c.parameters()):
-        p.grad = None
-    a0, a1 = x0.detach().cuda().requires_grad_(True), x1.detach().cuda().requires_grad_(True)
-    out = F2.conv_bn_act(a0, a1, conv_c, bn_c, 0.01)
-    out.backward(dy.cuda())
-    assert_close(out.detach().cpu(), ref.detach(), 2e-4, "block fwd")
-    assert_close(a0.grad.cpu(), x0.grad, 1e-3, "dx0")
-    assert_close(a1.grad.cpu(), x1.grad, 1e-3, "dx1")
-    assert_close(conv_c.weight.grad.cpu(), conv.weight.grad, 1e-3, "dw")
-    assert_close(bn_c.weight.grad.cpu(), bn.weight.grad, 1e-3, "dgamma")
-    assert_close(bn_c.bias.grad.cpu(), bn.bias.grad, 1e-3, "dbeta")
-    assert_close(bn_c.running_mean.cpu(), bn.running_mean, 1e-4, "running_mean", abs_floor=1e-6)
-    assert_close(bn_c.running_var.cpu(), bn.running_var, 1e-4, "running_var")
-    assert int(bn_c.num_batches_tracked) == 1
+    import icl_b200
+    import icl_b200.functional2d as F2
+    from icl_b200.networks.unet import UNet
+    K = 4
+    net = UNet(1, K)
+    synth.load_synth(net, 7)
+    net.cuda().train()
+    eval_dropout_only(net)
+    ref = copy.deepcopy(net).double()
+    x = synth.synth_volume((B, 1, size, size), 8).cuda()
+    y = synth.synth_labels((B, size, size), K, 9).cuda().long()
+    outs = []
+    orig = F2.conv_bn_act
+
+    def recording(*a, **kw):
+        o = orig(*a, **kw)
+        outs.append(o.detach().contiguous())
+        return o
+
+    monkeypatch.setattr(F2, "conv_bn_act", recording)
+    icl_b200.set_precision(mode)
+    try:
+        logits = net(x)
+        F.cross_entropy(logits, y).backward()
+    finally:
+        icl_b200.set_precision("parity")
+    assert len(outs) == 18
+    lr, nflip, nel = _replica_unet_forward(ref, x.double(), outs)
+    F.cross_entropy(lr, y).backward()
+    assert nflip <= max(3, 2e-5 * nel), "%d of %d discrete choices differ" % (nflip, nel)
+    assert_close(logits.detach().cpu(), lr.detach().cpu(), 5e-4, "logits")
+    rg = dict(ref.named_parameters())
+    for k, p in net.named_parameters():
+        gref = rg[k].grad
+        if k.endswith("conv_conv.0.bias") or k.endswith("conv_conv.4.bias"):  # followed by BatchNorm: exact gradient is 0
+            assert p.grad.abs().max().item() < 1e-6, k
+            continue
+        assert_close(p.grad.cpu(), gref.cpu(), 1e-3, k, abs_floor=1e-7)
 
 
 def test_maxpool2d_and_bilinear_ac_vs_torch():
@@ -96,7 +217,7 @@ def test_unet2d_golden():
     assert abs(loss.item() - float(gd["loss"])) < 5e-4 * float(gd["loss"])
     loss.backward()
     for k, p in net.named_parameters():
-        check_summary(p.grad, gd["gsum/" + k], gd["gval/" + k], 3e-3, k, abs_floor=2e-6)
+        check_summary(p.grad, gd["gsum/" + k], gd["gval/" + k], GRAD_FLIP_TOL, k, abs_floor=2e-6)
     for k, v in net.state_dict().items():
         if "running" in k:
             assert_close(v.cpu(), gd["stat/" + k], 1e-4, k, abs_floor=1e-6)
@@ -191,4 +312,4 @@ def test_full_step_2d_golden():
             assert p.grad is None, k
         else:
             assert p.grad is not None, k
-            check_summary(p.grad, gd["gsum/" + k], gd["gval/" + k], 5e-3, k, abs_floor=2e-6)
+            check_summary(p.grad, gd["gsum/" + k], gd["gval/" + k], GRAD_FLIP_TOL, k, abs_floor=2e-6)
