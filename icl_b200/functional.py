@@ -138,6 +138,40 @@ def proxy_attention(ql, kv, num_heads, want_xv=True):
     return ProxyAttnFn.apply(ql, kv, num_heads, want_xv)
 
 
+class WindowAttnFn(torch.autograd.Function):
+    """(Shifted-)window multi-head self-attention on token-major tensors (swinunet_icl.py:120-155 + the roll / partition /
+    reverse / mask of :249-293): qkv [B, H*W, 3C], relative-position table [(2ws-1)^2, nH] -> [B, H*W, C].
+    Probabilities are recomputed in backward; nothing but qkv is saved."""
+
+    @staticmethod
+    def forward(ctx, qkv, table, H, W, nH, ws, shift):
+        ops._require_cuda(qkv)
+        q_, t_ = _c(qkv.detach()), _c(table.detach())
+        B, L, C3 = q_.shape
+        if L != H * W or C3 % 3:
+            raise RuntimeError("window_attention: qkv %s does not match %dx%d tokens" % (tuple(q_.shape), H, W))
+        C = C3 // 3
+        out = torch.empty((B, L, C), dtype=torch.float32, device=q_.device)
+        call("icl_window_attn_fwd", P(q_), P(t_), P(out), c_int(B), c_int(H), c_int(W), c_int(C), c_int(nH), c_int(ws), c_int(shift))
+        ctx.save_for_backward(q_, t_)
+        ctx.dims = (B, H, W, C, nH, ws, shift)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        q_, t_ = ctx.saved_tensors
+        B, H, W, C, nH, ws, shift = ctx.dims
+        dqkv = torch.empty_like(q_)
+        dtable = torch.zeros_like(t_)
+        call("icl_window_attn_bwd", P(q_), P(t_), P(_c(dout)), P(dqkv), P(dtable), c_int(B), c_int(H), c_int(W), c_int(C), c_int(nH),
+             c_int(ws), c_int(shift))
+        return dqkv, dtable, None, None, None, None, None
+
+
+def window_attention(qkv, table, H, W, num_heads, window_size, shift):
+    return WindowAttnFn.apply(qkv, table, H, W, num_heads, window_size, shift)
+
+
 class AddScaledFn(torch.autograd.Function):
     """out = a + b * r  with r broadcast per leading-axis sample (DropPath residuals, unet_3D_icl.py:264-267);
     r is None in eval mode."""

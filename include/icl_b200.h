@@ -144,6 +144,14 @@ int icl_class_stats_bwd(const float* src, int planar, int rz, int ry, int rx, in
 int icl_softmax_mse(const float* a, const float* b, int B, int K, long long S, double* sum, const float* gup, float w, float* da, void* stream);
 int icl_scale_to_float(const double* s, double scale, float* out, void* stream);
 
+/* ---- Swin (shifted-)window attention: WindowAttention.forward networks/swinunet_icl.py:120-155 with the cyclic shift, window
+ * partition / reverse and shift mask of SwinTransformerBlock.forward :249-293 (mask :217-245) folded into the addressing.
+ * qkv [B, H*W, 3*C] token-major (channel = which*C + head*32 + d), table [(2*ws-1)^2, nH], out / dout [B, H*W, C];
+ * head_dim 32, ws*ws <= 64.  dtable must be zeroed by the caller (accumulated with atomics). ---- */
+int icl_window_attn_fwd(const float* qkv, const float* table, float* out, int B, int H, int W, int C, int nH, int ws, int shift, void* stream);
+int icl_window_attn_bwd(const float* qkv, const float* table, const float* dout, float* dqkv, float* dtable, int B, int H, int W, int C, int nH,
+                        int ws, int shift, void* stream);
+
 /* ---- optim.SGD(momentum=0.9, weight_decay=1e-4).step(): train_inherent_consistent_unet_3D_BraTS.py:85-86,115 ---- */
 int icl_sgd_multi(const void* tab, const int* chunk_tensor, const long long* chunk_off, int n_chunks, const float* lr_ptr, float mu, float wd,
                   int first, void* stream);

@@ -295,6 +295,71 @@ def gen_step2d(ns):
     print("step_cfg1 losses", {k: out[k] for k in ("ce", "dice", "aux", "pse", "cons", "total")}, "none", len(none), "time %.1fs" % (time.time() - t0))
 
 
+def swin_config():
+    """Effective values of configs/swin_tiny_patch4_window7_224_lite.yaml over networks/config.py defaults."""
+    from types import SimpleNamespace as NS
+    return NS(DATA=NS(IMG_SIZE=224), MODEL=NS(DROP_RATE=0.0, DROP_PATH_RATE=0.2, PRETRAIN_CKPT=None,
+              SWIN=NS(PATCH_SIZE=4, IN_CHANS=3, EMBED_DIM=96, DEPTHS=[2, 2, 2, 2], NUM_HEADS=[3, 6, 12, 24], WINDOW_SIZE=7, MLP_RATIO=4.0,
+                      QKV_BIAS=True, QK_SCALE=False, APE=False, PATCH_NORM=True)), TRAIN=NS(USE_CHECKPOINT=False))
+
+
+def gen_step_swin(ns, name, n_lab, n_unlab, seed):
+    """Config 4: SwinUnet(cfg, 224, 4) with the ICL heads, n_lab labeled + n_unlab unlabeled 1x224x224 slices, forward + the five
+    losses of train_inherent_consistent_swinunet_2D.py:148-155 + backward."""
+    t0 = time.time()
+    K = 4
+    m = ns.SwinUnet(swin_config(), img_size=224, num_classes=K)
+    synth.load_synth(m, seed)
+    m.train()
+    eval_dropout_only(m)
+    n = n_lab + n_unlab
+    x = synth.synth_volume((n, 1, 224, 224), seed + 1)
+    y = synth.synth_labels((n, 224, 224), K, seed + 2)
+    L = ns.losses
+    o = m(x[:n_lab], x[n_lab:])
+    ce = torch.nn.CrossEntropyLoss()(o[0], y[:n_lab].long())
+    dice = L.DiceLoss(K)(o[0], y[:n_lab].unsqueeze(1), softmax=True)
+    aux = L.AuxLoss(K)(o[2], y[:n_lab])
+    pse = L.PseudoSoftLoss(K)(o[3], o[1])
+    cons = L.softmax_mse_loss(o[3], o[4])
+    total = ce + dice + aux + pse + 50 * cons
+    total.backward()
+    out = dict(K=np.int64(K), n_lab=np.int64(n_lab), n_unlab=np.int64(n_unlab), seed=np.int64(seed), ce=ce.item(), dice=dice.item(),
+               aux=aux.item(), pse=pse.item(), cons=cons.item(), total=total.item())
+    for nm, t in (("out_lab", o[0]), ("out_unlab", o[1])):
+        sm, v = summarize(t.detach(), 4096)
+        out[nm + "_sum"], out[nm + "_val"] = sm, v
+        out[nm + "_argmax_count"] = np.bincount(t.argmax(1).reshape(-1).numpy(), minlength=K)
+    for j, nm in ((2, "maps_lab"), (3, "maps_unlab"), (4, "maps_consis")):
+        for i in range(3):
+            sm, v = summarize(o[j][i].detach(), 4096)
+            out["%s%d_sum" % (nm, i)], out["%s%d_val" % (nm, i)] = sm, v
+    none = []
+    for k, p in m.named_parameters():
+        if p.grad is None:
+            none.append(k)
+            continue
+        sm, v = summarize(p.grad)
+        out["gsum/" + k] = sm
+        out["gval/" + k] = v
+    out["grad_none"] = np.array(none)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "losses", {k: out[k] for k in ("ce", "dice", "aux", "pse", "cons", "total")}, "none", len(none), "time %.1fs" % (time.time() - t0))
+
+
+def gen_state_keys_2d_swin(ns):
+    """state_dict / parameter name+shape lists of the 2D and Swin models, merged into tests/golden/state_keys.json."""
+    import json
+    path = os.path.join(GOLDEN, "state_keys.json")
+    keys = json.load(open(path)) if os.path.exists(path) else {}
+    for name, m in (("unet_icl_k4", ns.UNet_icl(1, 4)), ("unet2d_k4", ns.UNet(1, 4)),
+                    ("swin_unet_k4", ns.SwinUnet(swin_config(), img_size=224, num_classes=4))):
+        keys[name] = [[k, list(v.shape)] for k, v in m.state_dict().items()]
+        keys[name + "_params"] = [k for k, _ in m.named_parameters()]
+    json.dump(keys, open(path, "w"))
+    print("state_keys:", sorted(keys.keys()))
+
+
 def gen_sliding(ns):
     tsc = ref_import.load_test_single_case()
     m = ns.unet_3D(feature_scale=4, n_classes=2, in_channels=1)
@@ -337,6 +402,9 @@ def main():
         "icl_head2d": lambda: gen_icl_head2d(ns),
         "losses2d": lambda: gen_losses2d(ns),
         "step_cfg1": lambda: gen_step2d(ns),
+        "state_keys_2d_swin": lambda: gen_state_keys_2d_swin(ns),
+        "step_swin_b2": lambda: gen_step_swin(ns, "step_swin_b2", 1, 1, 4401),
+        "step_cfg4": lambda: gen_step_swin(ns, "step_cfg4", 8, 8, 4404),
     }
     for k, fn in jobs.items():
         if a.only is None or a.only == k:

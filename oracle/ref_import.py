@@ -1,8 +1,8 @@
 """Import the UNMODIFIED reference (read-only, /root/reference/code) for oracle pinning.
 
 Only usable in the build container; the GPU box has no /root/reference.  Follows the recipe
-verified in SURVEY.md Appendix C: stub modules for monai first on sys.path, then the
-reference's ``code`` directory.  Never imports ``networks.net_factory*`` (argv parsing and
+verified in SURVEY.md Appendix C: stub modules for monai (and, for the Swin files, timm and turtle) first on sys.path,
+then the reference's ``code`` directory.  Never imports ``networks.net_factory*`` (argv parsing and
 missing modules at import, net_factory_3d.py:3-37).
 """
 import importlib
@@ -47,6 +47,12 @@ def load():
     ns.Encoder2d, ns.Decoder2d = m2.Encoder, m2.Decoder
     ns.InherentConsistent2d = m2.InherentConsistent
     ns.UNet = importlib.import_module("networks.unet").UNet
+    m3 = importlib.import_module("networks.vision_transformer")   # Swin path (config 4); timm / turtle come from oracle/stubs
+    ns.SwinUnet = m3.SwinUnet
+    ns.InherentConsistentTokens = m3.InherentConsistent
+    m4 = importlib.import_module("networks.swinunet_icl")
+    ns.SwinTransformerSys, ns.SwinTransformerBlock, ns.WindowAttention = m4.SwinTransformerSys, m4.SwinTransformerBlock, m4.WindowAttention
+    ns.PatchMerging, ns.PatchExpand, ns.FinalPatchExpand_X4, ns.PatchEmbed = m4.PatchMerging, m4.PatchExpand, m4.FinalPatchExpand_X4, m4.PatchEmbed
     ns.net_utils = importlib.import_module("networks.utils")
     ns.losses = importlib.import_module("utils.losses")
     return ns

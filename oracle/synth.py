@@ -54,11 +54,15 @@ def synth_tensor(name, shape, seed, idx, dtype=torch.float32):
     return torch.from_numpy(_uniform(rng, shape, 0.1))
 
 
+STRUCTURAL = ("relative_position_index", "attn_mask")  # Swin index / mask buffers: functions of the geometry, never synthesised
+
+
 def synth_state_dict(shapes, seed):
     """shapes: OrderedDict name -> shape (e.g. from model.state_dict()).  Returns name -> tensor."""
     out = OrderedDict()
     for idx, (name, shape) in enumerate(shapes.items()):
-        out[name] = synth_tensor(name, shape, seed, idx)
+        if not name.endswith(STRUCTURAL):
+            out[name] = synth_tensor(name, shape, seed, idx)
     return out
 
 
@@ -71,6 +75,8 @@ def load_synth(model, seed):
     sd = model.state_dict()
     with torch.no_grad():
         for idx, (name, t) in enumerate(sd.items()):
+            if name.endswith(STRUCTURAL):
+                continue
             v = synth_tensor(name, t.shape, seed, idx)
             t.copy_(v.to(t.dtype))
     return model
