@@ -271,6 +271,61 @@ __global__ void instnorm_relu_bwd_apply_k(const float* __restrict__ dA, const fl
     }
   }
 }
+// Same arithmetic with the 8-channel group as the FASTEST thread index (C/8 a power of two <= 32): consecutive lanes read
+// consecutive 32-byte segments of a voxel, so every DRAM line is fetched once.  With one CTA per channel group (kernel above)
+// the two groups of a C = 16 layer run in different waves and each 64-byte line of dA / y was read from DRAM twice
+// (ncu r01p: 448 MB read for 226 MB of operands).
+__global__ void __launch_bounds__(256, 3) instnorm_relu_bwd_apply_cl_k(
+    const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr, const double* __restrict__ red,
+    float* __restrict__ dY, __nv_bfloat16* __restrict__ pk, int write_lo, int B, int C, long long S, float* __restrict__ dbias,
+    const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
+  __shared__ float bsum[8][32][8];
+  const int C8 = C >> 3;
+  const int b = blockIdx.y, c8 = threadIdx.x & (C8 - 1);
+  float mean[8], rstd[8], mg[8], mgy[8], gm[8], bt[8], bacc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long k = (long long)b * C + c8 * 8 + i;
+    mean[i] = mr[k * 2]; rstd[i] = mr[k * 2 + 1];
+    mg[i] = (float)(red[k * 2] / (double)S); mgy[i] = (float)(red[k * 2 + 1] / (double)S);
+    gm[i] = gamma ? gamma[c8 * 8 + i] : 1.f; bt[i] = beta ? beta[c8 * 8 + i] : 0.f;
+    bacc[i] = 0.f;
+  }
+  const long long plane = (long long)B * C8 * S * 8;
+  __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
+  const long long total = S * C8;  // (voxel, group) pairs of this sample; blockDim and the grid stride are multiples of C8
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long s = i / C8;
+    const long long off = ((long long)b * S + s) * C + c8 * 8;
+    float yv[8], gv[8], o[8];
+    unpack8(ld8(y + off), yv);
+    unpack8(ld8(dA + off), gv);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float yh = (yv[j] - mean[j]) * rstd[j];
+      const float g = gv[j] * act_grad(yh, gm[j], bt[j], slope);
+      o[j] = rstd[j] * gm[j] * (g - mg[j] - yh * mgy[j]);
+      bacc[j] += o[j];
+    }
+    if (dY) st8(dY + off, o);
+    if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, o);
+  }
+  if (dbias) {  // lanes l and l + C8 own the same channels: fold them, then warps -> block -> one atomic per channel
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      float t = bacc[j];
+      for (int o2 = 16; o2 >= C8; o2 >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o2);
+      if (lane < C8) bsum[wid][lane][j] = t;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 8; i += blockDim.x) {
+      float t = 0.f;
+      for (int w = 0; w < 8; ++w) t += bsum[w][i >> 3][i & 7];
+      atomicAdd(dbias + i, t);
+    }
+  }
+}
 __global__ void instnorm_relu_bwd_apply_generic_k(const float* __restrict__ dA, const float* __restrict__ y, const float* __restrict__ mr,
                                                   const double* __restrict__ red, float* __restrict__ dY, int C, long long S, long long total,
                                                   const float* __restrict__ gamma, const float* __restrict__ beta, float slope) {
@@ -289,11 +344,16 @@ ICL_API int icl_normact_bwd(const float* dA, const float* y, const float* mr, co
                             double* red /* [B,C,2] zeroed; out: sum g' (= dbeta), sum g' yh (= dgamma) */, float* dY, void* pk, int write_lo,
                             float* dbias /* [C] zeroed, or null */, int B, int C, long long S, void* stream) {
   ICL_REQUIRE(C <= 1024, "normact_bwd: C=%d > 1024", C);
-  int chunks = (int)min((long long)max(1, 148 * 4 / B), (S * C + 16383) / 16384);
+  // one wave: the reduce kernel holds 3 CTAs per SM (66 registers); 592 CTAs ran as 1.33 waves (ncu r01p)
+  int chunks = (int)min((long long)max(1, 148 * 3 / B), (S * C + 16383) / 16384);
   if (chunks < 1) chunks = 1;
   instnorm_relu_bwd_reduce_k<<<dim3(chunks, B), 256, 2 * C * sizeof(double), as_stream(stream)>>>(dA, y, mr, red, C, S, chunks, gamma, beta, slope);
   icl_count_launch(1);
-  if (C % 8 == 0) {
+  const int C8 = C / 8;
+  if (C % 8 == 0 && C8 <= 32 && (C8 & (C8 - 1)) == 0) {
+    int gx = (int)min((long long)cdiv(S * C8, 256), (long long)max(1, 148 * 3 / B));
+    instnorm_relu_bwd_apply_cl_k<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S, dbias, gamma, beta, slope);
+  } else if (C % 8 == 0) {
     int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));
     instnorm_relu_bwd_apply_k<<<dim3(gx, B * (C / 8)), 256, 0, as_stream(stream)>>>(dA, y, mr, red, dY, (__nv_bfloat16*)pk, write_lo, B, C, S, dbias, gamma, beta, slope);
   } else {

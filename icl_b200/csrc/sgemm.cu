@@ -344,6 +344,104 @@ __global__ void __launch_bounds__(128) skinny_nt_k(int M, int N, int K, const fl
       }
     }
 }
+// skinny NT, second form: the WEIGHTS are the MMA A operand (16 weight rows per m16 tile, RW tiles per warp) and the activations
+// the B operand (8 activation rows per n8 tile), so one set of shared-memory B fragments serves RW*16 weight rows instead of 8:
+// 4x fewer shared-memory wavefronts and 4x less activation re-staging per weight byte than skinny_nt_k (ncu r01p: that kernel
+// sat at 51 % of the shared-memory pipe and 57 % issue for 2.6 TB/s of weight stream).
+// k-slot mapping as above: MMA k-slot t <- column 32u + 8t + 2s, k-slot t+4 <- column 32u + 8t + 2s + 1, so a lane's A
+// fragment comes from its own two 32-byte weight segments and nothing is shuffled.
+#define S2_KC 64                 // K per register chunk of weights: RW*16 rows x 64 floats in flight per warp
+#define S2_XC 256                // K per staged activation chunk
+#define S2_LD (S2_XC + 2)
+template <int RW, int NT>
+__global__ void __launch_bounds__(128) skinny_nt2_k(int M, int N, int K, const float* __restrict__ x, const float* __restrict__ Wt,
+                                                    const float* __restrict__ bias, float* __restrict__ y, float* __restrict__ pre, int act,
+                                                    int k_per) {
+  extern __shared__ __align__(16) uint32_t sk_smem[];
+  uint32_t* xh = sk_smem;                       // [NT*8][S2_LD] tf32 hi
+  uint32_t* xl = sk_smem + NT * 8 * S2_LD;      // [NT*8][S2_LD] tf32 lo
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int n0 = (blockIdx.x * 4 + wid) * (RW * 16);
+  const float* wrow[2 * RW];
+#pragma unroll
+  for (int r = 0; r < 2 * RW; ++r) wrow[r] = Wt + (long long)min(n0 + g + 8 * r, N - 1) * K;  // clamp: rows past N are never stored
+  float acc[RW][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < RW; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[mt][nt][0] = acc[mt][nt][1] = acc[mt][nt][2] = acc[mt][nt][3] = 0.f;
+  const int kbeg = blockIdx.y * k_per, kend = min(K, kbeg + k_per);
+  for (int k0 = kbeg; k0 < kend; k0 += S2_XC) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < NT * 8 * (S2_XC / 4); i += 128) {
+      const int m = i / (S2_XC / 4), kq = (i % (S2_XC / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (m < M && k0 + kq < kend) v = *reinterpret_cast<const float4*>(x + (long long)m * K + k0 + kq);
+      uint4 h, l;
+      split_tf32(v.x, h.x, l.x); split_tf32(v.y, h.y, l.y); split_tf32(v.z, h.z, l.z); split_tf32(v.w, h.w, l.w);
+      *reinterpret_cast<uint2*>(&xh[m * S2_LD + kq]) = make_uint2(h.x, h.y);
+      *reinterpret_cast<uint2*>(&xh[m * S2_LD + kq + 2]) = make_uint2(h.z, h.w);
+      *reinterpret_cast<uint2*>(&xl[m * S2_LD + kq]) = make_uint2(l.x, l.y);
+      *reinterpret_cast<uint2*>(&xl[m * S2_LD + kq + 2]) = make_uint2(l.z, l.w);
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int kc = 0; kc < S2_XC && k0 + kc < kend; kc += S2_KC) {
+      float4 wv[2 * RW][S2_KC / 32][2];
+#pragma unroll
+      for (int r = 0; r < 2 * RW; ++r)
+#pragma unroll
+        for (int u = 0; u < S2_KC / 32; ++u) {
+          const int k = k0 + kc + u * 32 + 8 * t;
+          wv[r][u][0] = (k < kend) ? __ldg(reinterpret_cast<const float4*>(wrow[r] + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          wv[r][u][1] = (k + 4 < kend) ? __ldg(reinterpret_cast<const float4*>(wrow[r] + k + 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+      for (int u = 0; u < S2_KC / 32; ++u) {
+#pragma unroll
+        for (int sidx = 0; sidx < 4; ++sidx) {
+          const int col = kc + u * 32 + 8 * t + 2 * sidx;
+          uint2 bh[NT], bl[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            bh[nt] = *reinterpret_cast<const uint2*>(&xh[(nt * 8 + g) * S2_LD + col]);
+            bl[nt] = *reinterpret_cast<const uint2*>(&xl[(nt * 8 + g) * S2_LD + col]);
+          }
+#pragma unroll
+          for (int mt = 0; mt < RW; ++mt) {
+            const float4 q0 = wv[2 * mt][u][sidx >> 1], q1 = wv[2 * mt + 1][u][sidx >> 1];
+            const float w00 = (sidx & 1) ? q0.z : q0.x, w01 = (sidx & 1) ? q0.w : q0.y;   // row g      : columns col, col + 1
+            const float w10 = (sidx & 1) ? q1.z : q1.x, w11 = (sidx & 1) ? q1.w : q1.y;   // row g + 8
+            uint32_t a0h, a0l, a1h, a1l, a2h, a2l, a3h, a3l;
+            split_tf32(w00, a0h, a0l); split_tf32(w10, a1h, a1l); split_tf32(w01, a2h, a2l); split_tf32(w11, a3h, a3l);
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) {
+              mma_tf32(acc[mt][nt], a0h, a1h, a2h, a3h, bh[nt].x, bh[nt].y);
+              mma_tf32(acc[mt][nt], a0l, a1l, a2l, a3l, bh[nt].x, bh[nt].y);
+              mma_tf32(acc[mt][nt], a0h, a1h, a2h, a3h, bl[nt].x, bl[nt].y);
+            }
+          }
+        }
+      }
+    }
+  }
+  // C fragment of tile (mt, nt): c0 (weight row g, activation row 2t), c1 (g, 2t+1), c2 (g+8, 2t), c3 (g+8, 2t+1)
+#pragma unroll
+  for (int mt = 0; mt < RW; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int n = n0 + mt * 16 + g + (i >> 1) * 8, m = nt * 8 + 2 * t + (i & 1);
+        if (m < M && n < N) {
+          const long long o = (long long)m * N + n;
+          if (gridDim.y > 1) { atomicAdd(y + o, acc[mt][nt][i]); continue; }
+          float v = acc[mt][nt][i] + (bias ? bias[n] : 0.f);
+          if (pre) pre[o] = v;
+          y[o] = act == 1 ? gelu_erf(v) : v;
+        }
+      }
+}
 __global__ void skinny_bias_act_k(float* __restrict__ y, float* __restrict__ pre, const float* __restrict__ bias, long long total, int N, int act) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const float v = y[i] + (bias ? bias[i % N] : 0.f);
@@ -354,19 +452,20 @@ __global__ void skinny_bias_act_k(float* __restrict__ y, float* __restrict__ pre
 ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
                                   void* stream) {
   ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0, "skinny_linear_fwd: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
-  const int gx = cdiv(N, 32);
-  // K split so that ~8 CTAs per SM are in flight (K % 4 == 0 and kend multiples of SK_KC keep the float4 loads aligned)
-  int ksplit = 1, k_per = K;
-  if (K >= 4 * SK_KC && gx < 148 * 8) {
-    ksplit = (148 * 8 + gx - 1) / gx;
-    if (ksplit > K / (2 * SK_KC)) ksplit = K / (2 * SK_KC);
-    if (ksplit > 16) ksplit = 16;
-    if (ksplit < 1) ksplit = 1;
-    k_per = cdiv(cdiv(K, ksplit), SK_KC) * SK_KC;
-    ksplit = cdiv(K, k_per);
-  }
-  if (ksplit > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, as_stream(stream));
-  const dim3 grid(gx, ksplit);
+  if ((long long)N * K < (1LL << 24)) {
+    // small weight matrices: 8 rows per warp (more, smaller CTAs) keeps more of the machine busy
+    const int gx = cdiv(N, 32);
+    int ksplit = 1, k_per = K;
+    if (K >= 4 * SK_KC && gx < 148 * 8) {
+      ksplit = (148 * 8 + gx - 1) / gx;
+      if (ksplit > K / (2 * SK_KC)) ksplit = K / (2 * SK_KC);
+      if (ksplit > 16) ksplit = 16;
+      if (ksplit < 1) ksplit = 1;
+      k_per = cdiv(cdiv(K, ksplit), SK_KC) * SK_KC;
+      ksplit = cdiv(K, k_per);
+    }
+    if (ksplit > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, as_stream(stream));
+    const dim3 grid(gx, ksplit);
 #define SK_LAUNCH(MT)                                                                                                    \
   {                                                                                                                      \
     const size_t smem = (size_t)2 * MT * 16 * SK_LD * 4;                                                                 \
@@ -374,8 +473,38 @@ ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const flo
     if (!cfg) { cudaFuncSetAttribute(skinny_nt_k<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg = true; } \
     skinny_nt_k<MT><<<grid, 128, smem, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act, k_per);                          \
   }
-  if (M <= 16) SK_LAUNCH(1) else if (M <= 32) SK_LAUNCH(2) else SK_LAUNCH(4)
+    if (M <= 16) SK_LAUNCH(1) else if (M <= 32) SK_LAUNCH(2) else SK_LAUNCH(4)
 #undef SK_LAUNCH
+    if (ksplit > 1) {
+      icl_count_launch(1);
+      skinny_bias_act_k<<<grid_for((long long)M * N, 256), 256, 0, as_stream(stream)>>>(y, pre, bias, (long long)M * N, N, act);
+    }
+    ICL_LAUNCHED("skinny_linear_fwd");
+  }
+  // large weight matrices (mlp2 at 24^3: 13824 x 13824): weights as the A operand, RW m16 tiles per warp
+  const int RW = M <= 32 ? 2 : 1;
+  const int gx = cdiv(N, 64 * RW);
+  // K split: as many CTAs as stay resident at once (5 per SM at 90 registers) — measured on 16 x 13824 x 13824: 648 CTAs
+  // 0.198 ms, 432 CTAs (better balanced, fewer bytes in flight) 0.218 ms.  kend multiples of S2_XC keep the float4 loads aligned.
+  int ksplit = 1, k_per = K;
+  for (int ks = 2; ks <= 16 && ks * 2 * S2_XC <= K; ++ks) {
+    const int kp = cdiv(cdiv(K, ks), S2_XC) * S2_XC;
+    if (gx * cdiv(K, kp) > 148 * 5) break;
+    ksplit = cdiv(K, kp); k_per = kp;
+  }
+  if (ksplit > 1) cudaMemsetAsync(y, 0, sizeof(float) * (size_t)M * N, as_stream(stream));
+  const dim3 grid(gx, ksplit);
+#define S2_LAUNCH(RW_, NT_)                                                                                                      \
+  {                                                                                                                              \
+    const size_t smem = (size_t)2 * NT_ * 8 * S2_LD * 4;                                                                         \
+    static bool cfg = false;                                                                                                     \
+    if (!cfg) { cudaFuncSetAttribute(skinny_nt2_k<RW_, NT_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); cfg = true; } \
+    skinny_nt2_k<RW_, NT_><<<grid, 128, smem, as_stream(stream)>>>(M, N, K, x, Wt, bias, y, pre, act, k_per);                      \
+  }
+  if (M <= 16) { if (RW == 2) S2_LAUNCH(2, 2) else S2_LAUNCH(1, 2) }
+  else if (M <= 32) { if (RW == 2) S2_LAUNCH(2, 4) else S2_LAUNCH(1, 4) }
+  else S2_LAUNCH(1, 8)
+#undef S2_LAUNCH
   if (ksplit > 1) {
     icl_count_launch(1);
     skinny_bias_act_k<<<grid_for((long long)M * N, 256), 256, 0, as_stream(stream)>>>(y, pre, bias, (long long)M * N, N, act);

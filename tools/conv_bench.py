@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Micro-benchmark of the tcgen05 implicit-GEMM convolution at the unet_3D layer shapes.
 
-    python tools/conv_bench.py [--precision parity|fast] [--only NAME] [--iters N]
+    python tools/conv_bench.py [--precision parity|fast] [--only NAME] [--iters N] [--wgrad]
 
 Prints per layer: time per launch (CUDA events on the launching stream, inputs > L2 or L2 flushed between
 launches), algorithmic TFLOP/s and the fraction of the measured bf16 peak.  Used under `ncu --set full -k regex:conv3d_umma`."""
@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--precision", default="parity")
     ap.add_argument("--only", default="")
     ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--wgrad", action="store_true", help="time the weight-gradient kernel (conv3d_wgrad_umma.cu) instead of the forward")
     a = ap.parse_args()
     import icl_b200
     from icl_b200 import ops
@@ -46,14 +47,21 @@ def main():
         bias = torch.zeros(cout, device="cuda")
         stats = torch.zeros(B, cout, 2, dtype=torch.float64, device="cuda")
         out = torch.empty(B, r, r, r, cout, device="cuda")
+        if a.wgrad:
+            if name.endswith("dgrad") or r % 2:
+                continue
+            dy_pk = ops.pack_pk(torch.randn(B, r, r, r, cout, device="cuda", generator=g))
+            run = lambda: ops.conv3d_wgrad_umma(pks, cins, dy_pk, cout, B, r, r, r)
+        else:
+            run = lambda: ops.conv3d_umma(pks, cins, wp, bias, cout, B, r, r, r, stats, out=out)
         for _ in range(3):
-            ops.conv3d_umma(pks, cins, wp, bias, cout, B, r, r, r, stats, out=out)
+            run()
         ts = []
         for _ in range(a.iters):
             flush.zero_()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
-            ops.conv3d_umma(pks, cins, wp, bias, cout, B, r, r, r, stats, out=out)
+            run()
             e1.record()
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1))
@@ -61,7 +69,7 @@ def main():
         ms = ts[len(ts) // 2]
         gf = 2e-9 * 27 * sum(cins) * cout * B * r ** 3
         tf = gf / ms
-        print("%-18s B%d r%-3d %-9s->%-3d  %8.3f ms  %7.1f TFLOP/s algorithmic  %5.1f%% of measured bf16 peak (%s)" % (
+        print(("wgrad " if a.wgrad else "") + "%-18s B%d r%-3d %-9s->%-3d  %8.3f ms  %7.1f TFLOP/s algorithmic  %5.1f%% of measured bf16 peak (%s)" % (
             name, B, r, "+".join(map(str, cins)), cout, ms, tf, 100 * tf / peak, a.precision), flush=True)
 
 
