@@ -706,9 +706,54 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_v8_k(const float* __restri
     if (hi) st_pk8(hi + s * 8, write_lo ? hi + plane + s * 8 : nullptr, r);
   }
 }
+// Same with the 8-channel group as the fastest thread index (C/8 a power of two <= 32, S * C/8 < 2^31): neighbouring lanes read
+// neighbouring 32-byte segments of the same coarse voxel, so a corner load touches C/32 lines per voxel instead of one line per
+// lane (the kernel above needs 32 L1 wavefronts per 128-bit request at C = 32), and the index arithmetic is 32-bit.
+__global__ void __launch_bounds__(256) upsample2x_fwd_cl_k(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ pk,
+                                                           int write_lo, int B, int C, int d, int h, int w, int c8_log2) {
+  const int D = 2 * d, H = 2 * h, W = 2 * w, C8 = C >> 3;
+  const long long S = (long long)D * H * W;
+  const int b = blockIdx.y, c8 = threadIdx.x & (C8 - 1);
+  const long long plane = (long long)B * C8 * S * 8;
+  const float* xb = x + (long long)b * d * h * w * C + c8 * 8;
+  __nv_bfloat16* hi = pk ? pk + ((long long)b * C8 + c8) * S * 8 : nullptr;
+  float* ob = out ? out + (long long)b * S * C + c8 * 8 : nullptr;
+  const unsigned total = (unsigned)(S << c8_log2);
+  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const unsigned s = i >> c8_log2;
+    const unsigned q = s / (unsigned)W;
+    const int X = (int)(s - q * (unsigned)W), Z = (int)(q / (unsigned)H), Y = (int)(q - (unsigned)Z * (unsigned)H);
+    int z0, z1, y0, y1, x0, x1; float lz, ly, lx;
+    up2_src(Z, d, z0, z1, lz); up2_src(Y, h, y0, y1, ly); up2_src(X, w, x0, x1, lx);
+    float c[8][8];
+#define LD(i_, zz, yy, xx) unpack8(ld8(xb + (size_t)(((zz) * h + (yy)) * w + (xx)) * C), c[i_])
+    LD(0, z0, y0, x0); LD(1, z0, y0, x1); LD(2, z0, y1, x0); LD(3, z0, y1, x1);
+    LD(4, z1, y0, x0); LD(5, z1, y0, x1); LD(6, z1, y1, x0); LD(7, z1, y1, x1);
+#undef LD
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      // same association order as ATen's upsample_trilinear3d: w-lerp inside h-lerp inside d-lerp
+      const float v00 = (1.f - lx) * c[0][j] + lx * c[1][j], v01 = (1.f - lx) * c[2][j] + lx * c[3][j];
+      const float v10 = (1.f - lx) * c[4][j] + lx * c[5][j], v11 = (1.f - lx) * c[6][j] + lx * c[7][j];
+      r[j] = (1.f - lz) * ((1.f - ly) * v00 + ly * v01) + lz * ((1.f - ly) * v10 + ly * v11);
+    }
+    if (ob) st8(ob + (size_t)s * C, r);
+    if (hi) st_pk8(hi + (size_t)s * 8, write_lo ? hi + plane + (size_t)s * 8 : nullptr, r);
+  }
+}
 ICL_API int icl_upsample2x_fwd(const float* x, float* out, void* pk, int write_lo, int B, int C, int d, int h, int w, void* stream) {
   ICL_REQUIRE(pk == nullptr || C % 8 == 0, "upsample2x: PK output needs C %% 8 == 0");
   ICL_REQUIRE(pk != nullptr || out != nullptr, "upsample2x: no output requested");
+  const int C8u = C / 8;
+  if (C % 8 == 0 && C8u <= 32 && (C8u & (C8u - 1)) == 0 && 8LL * d * h * w * C8u < (1LL << 31)) {
+    const long long S = 8LL * d * h * w;
+    int lg = 0;
+    while ((1 << lg) < C8u) ++lg;
+    int gx = (int)min((long long)cdiv(S * C8u, 256), (long long)max(1, 148 * 8 / B));
+    upsample2x_fwd_cl_k<<<dim3(gx, B), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, B, C, d, h, w, lg);
+    ICL_LAUNCHED("upsample2x_fwd");
+  }
   if (C % 8 == 0) {
     const long long S = 8LL * d * h * w;
     int gx = (int)min((long long)cdiv(S, 256), (long long)max(1, 148 * 8 / (B * (C / 8)) + 1));

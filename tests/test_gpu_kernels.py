@@ -287,7 +287,7 @@ def test_maxpool_ties_first_max():
     assert_close(dx2.cpu(), (base + cl(xr.grad)).cpu(), 1e-6, "accumulate")
 
 
-@pytest.mark.parametrize("C", [16, 6])
+@pytest.mark.parametrize("C", [16, 6, 64, 24])
 def test_upsample2x_fwd_bwd(C):
     ops = _ops()
     B, d, h, w = 2, 3, 4, 5
