@@ -516,6 +516,7 @@ ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const flo
 // range is split over blockIdx.y and combined with atomics.  Warp = 32 output columns (4 MMA column tiles sharing the
 // A fragment: a weight float4 at [n][kb + 4g .. 4g+3] feeds column g of tiles 0..3), block = 4 warps = 128 columns.
 #define SN_NC 256
+#define SN_UB 4
 #define SN_LD (SN_NC + 4)  // 4*g + t -> conflict-free 32-bit fragment loads
 template <int MT>
 __global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const float* __restrict__ dy, const float* __restrict__ Wt,
@@ -542,16 +543,16 @@ __global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const fl
     __syncthreads();
     const int steps = min(SN_NC, nend - n0 + 7) / 8;  // rows past nend multiply zeroed dy (weights clamped in range)
 #pragma unroll 1
-    for (int s0 = 0; s0 < steps; s0 += 4) {
-      float4 w0[4], w1[4];
+    for (int s0 = 0; s0 < steps; s0 += SN_UB) {
+      float4 w0[SN_UB], w1[SN_UB];   // SN_UB steps of 8 weight rows in flight per warp (8 KB)
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SN_UB; ++u) {
         const int r0 = min(n0 + (s0 + u) * 8 + t, N - 1), r1 = min(n0 + (s0 + u) * 8 + t + 4, N - 1);
         w0[u] = __ldg(reinterpret_cast<const float4*>(Wt + (long long)r0 * K + kcol));
         w1[u] = __ldg(reinterpret_cast<const float4*>(Wt + (long long)r1 * K + kcol));
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < SN_UB; ++u) {
         if (s0 + u >= steps) break;
         const int nl = (s0 + u) * 8;
         const float f0[4] = {w0[u].x, w0[u].y, w0[u].z, w0[u].w}, f1[4] = {w1[u].x, w1[u].y, w1[u].z, w1[u].w};
@@ -592,6 +593,7 @@ __global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const fl
 ICL_API int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream) {
   ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0 && K >= 4, "skinny_linear_dgrad: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
   const int gx = cdiv(K, 128);
+  // all CTAs resident at once (6 per SM at 78 registers / 33 KB): more would run as a partial second wave
   int splits = max(1, min(cdiv(N, SN_NC), (148 * 6) / gx));
   const int n_per = cdiv(cdiv(N, splits), SN_NC) * SN_NC;
   splits = cdiv(N, n_per);
