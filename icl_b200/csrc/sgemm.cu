@@ -449,9 +449,8 @@ __global__ void skinny_bias_act_k(float* __restrict__ y, float* __restrict__ pre
     y[i] = act == 1 ? gelu_erf(v) : v;
   }
 }
-ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
-                                  void* stream) {
-  ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0, "skinny_linear_fwd: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
+static int skinny_fwd_rows(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
+                           void* stream) {
   if ((long long)N * K < (1LL << 24)) {
     // small weight matrices: 8 rows per warp (more, smaller CTAs) keeps more of the machine busy
     const int gx = cdiv(N, 32);
@@ -510,6 +509,18 @@ ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const flo
     skinny_bias_act_k<<<grid_for((long long)M * N, 256), 256, 0, as_stream(stream)>>>(y, pre, bias, (long long)M * N, N, act);
   }
   ICL_LAUNCHED("skinny_linear_fwd");
+}
+
+ICL_API int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act,
+                                  void* stream) {
+  ICL_REQUIRE(M >= 1 && M <= 256 && K % 4 == 0, "skinny_linear_fwd: need 1 <= M <= 256 and K %% 4 == 0 (M=%d K=%d)", M, K);
+  // more than 64 rows (config 3: K = 16 classes x 4 heads x 2 samples = 128): one weight pass per block of 64 rows
+  for (int m0 = 0; m0 < M; m0 += 64) {
+    const int rc = skinny_fwd_rows(min(64, M - m0), N, K, x + (size_t)m0 * K, Wt, bias, y + (size_t)m0 * N, pre ? pre + (size_t)m0 * N : nullptr,
+                                   act, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 // skinny NN (data gradient):  dx[m, k] += sum_n dy[m, n] * W[n, k],  M <= 16*MT.  dx must be zeroed by the caller; the n
@@ -590,8 +601,7 @@ __global__ void __launch_bounds__(128) skinny_nn_k(int M, int N, int K, const fl
         if (m < M && k < K) atomicAdd(dx + (long long)m * K + k, acc[mt][j][i]);
       }
 }
-ICL_API int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream) {
-  ICL_REQUIRE(M >= 1 && M <= 64 && K % 4 == 0 && K >= 4, "skinny_linear_dgrad: need 1 <= M <= 64 and K %% 4 == 0 (M=%d K=%d)", M, K);
+static int skinny_dgrad_rows(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream) {
   const int gx = cdiv(K, 128);
   // all CTAs resident at once (6 per SM at 78 registers / 33 KB): more would run as a partial second wave
   int splits = max(1, min(cdiv(N, SN_NC), (148 * 6) / gx));
@@ -607,6 +617,15 @@ ICL_API int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const 
   if (M <= 16) SN_LAUNCH(1) else if (M <= 32) SN_LAUNCH(2) else SN_LAUNCH(4)
 #undef SN_LAUNCH
   ICL_LAUNCHED("skinny_linear_dgrad");
+}
+
+ICL_API int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream) {
+  ICL_REQUIRE(M >= 1 && M <= 256 && K % 4 == 0 && K >= 4, "skinny_linear_dgrad: need 1 <= M <= 256 and K %% 4 == 0 (M=%d K=%d)", M, K);
+  for (int m0 = 0; m0 < M; m0 += 64) {
+    const int rc = skinny_dgrad_rows(min(64, M - m0), N, K, dy + (size_t)m0 * N, Wt, dx + (size_t)m0 * K, stream);
+    if (rc) return rc;
+  }
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -107,7 +107,8 @@ int icl_row_combine(const float* a, const float* sa, const float* b, const float
 int icl_sgemm(int M, int N, int K, const float* A, long long sam, long long sak, long long sA, const float* Bm, long long sbk, long long sbn,
               long long sB, float* C, long long scm, long long scn, long long sC, int batch, const float* bias, int bias_mode, int act,
               int accumulate, float* pre, void* stream);
-/* mlp2 = MLP(N, N, N) over the spatial axis, networks/unet_3D_icl.py:258-259,267: weight-streaming kernels */
+/* mlp2 = MLP(N, N, N) over the spatial axis, networks/unet_3D_icl.py:258-259,267: weight-streaming kernels; M <= 256 rows
+ * (one weight pass per block of 64 rows), K % 4 == 0 */
 int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act, void* stream);
 int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream);
 int icl_outer_wgrad(int M, int N, int K, const float* dy, const float* x, float* dW, float* db, int accumulate, void* stream);

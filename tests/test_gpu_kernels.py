@@ -331,7 +331,7 @@ def test_dropout_mask_and_philox():
 # ------------------------------------------------------------------------------------------ GEMM family / heads
 @pytest.mark.parametrize("M,N,K", [(7, 33, 19), (130, 70, 65), (16, 2048, 1024), (3, 1030, 1100), (40, 1536, 1536), (32, 1728, 1728),
                                    (16, 1100, 2052), (64, 1027, 1028), (16, 4100, 2052), (24, 4608, 1028), (5, 4097, 260), (16, 8200, 2052),
-                                   (24, 4608, 4100), (40, 4224, 4100)])
+                                   (24, 4608, 4100), (40, 4224, 4100), (100, 4224, 4100), (128, 4100, 4224)])
 def test_linear_fwd_bwd(M, N, K):
     import icl_b200.functional as Fn
     x = torch.randn(M, K, generator=g(1), requires_grad=True)
