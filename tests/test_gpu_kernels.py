@@ -351,6 +351,22 @@ def test_linear_fwd_bwd(M, N, K):
         assert_close(bc.grad.cpu(), gb, 2e-5, "linear db")
 
 
+def test_skinny_linear_abi_row_blocks():
+    """The C-ABI skinny GEMMs take up to 256 rows (one weight pass per 64-row block); Python routes > 64 rows elsewhere."""
+    from icl_b200.ops import P, c_int, call
+    M, N, K = 100, 1100, 1028
+    x = torch.randn(M, K, generator=g(1)).cuda()
+    w = (torch.randn(N, K, generator=g(2)) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g(3)).cuda()
+    y = torch.empty(M, N, device="cuda")
+    call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x), P(w), P(b), P(y), P(None), c_int(0))
+    assert_close(y.cpu(), F.linear(x.double(), w.double(), b.double()).cpu(), 2e-5, "skinny fwd 100 rows")
+    dy = torch.randn(M, N, generator=g(4)).cuda()
+    dx = torch.zeros(M, K, device="cuda")
+    call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy), P(w), P(dx))
+    assert_close(dx.cpu(), (dy.double() @ w.double()).cpu(), 2e-5, "skinny dgrad 100 rows")
+
+
 @pytest.mark.parametrize("M,N,K", [(100000, 16, 2), (70001, 64, 64), (33000, 128, 64)])
 def test_linear_long_reduction_splitk(M, N, K):
     """1x1x1-conv / Linear weight and bias gradients reduce over all voxels: split-K sgemm + parallel column sums
