@@ -1,0 +1,57 @@
+#!/usr/bin/env python
+"""Time one training step (forward + the five ICL losses + backward, no optimizer) of BASELINE config 1 (2D UNet_icl, 12 + 12
+slices of 1x256x256) and config 4 (Swin-UNet ICL, 8 + 8 slices of 1x224x224) on cuda:0 with CUDA events."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from icl_b200.utils import losses as L  # noqa: E402
+from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
+
+
+def run(name, net, x, y, n_lab, size, iters=5):
+    K = 4
+    net.cuda().train()
+    aux, pse = L.AuxLoss(K, resize=[size, size]), L.PseudoSoftLoss(K, resize=[size, size])
+    ce_l, dice_l = L.CrossEntropyLoss(), L.DiceLoss(K)
+
+    def step():
+        for p in net.parameters():
+            p.grad = None
+        o = net(x[:n_lab], x[n_lab:])
+        loss = ce_l(o[0], y[:n_lab].long()) + dice_l(o[0], y[:n_lab].unsqueeze(1), softmax=True) + aux(o[2], y[:n_lab]) \
+            + pse(o[3], o[1]) + 50 * L.softmax_mse_loss(o[3], o[4])
+        loss.backward()
+        return loss
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(); loss = step(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ms = sorted(ts)[len(ts) // 2]
+    print("%s: %.1f ms/step (fwd + 5 losses + bwd, eager), %.0f slices/s, loss %.4f" % (name, ms, 1e3 * x.shape[0] / ms, loss.item()), flush=True)
+
+
+def main():
+    from icl_b200.networks.unet_icl import UNet_icl
+    from icl_b200.networks.vision_transformer import SwinUnet, swin_tiny_lite_config
+    net = UNet_icl(1, 4)
+    synth.load_synth(net, 1337)
+    run("config 1 (UNet_icl, 24 x 1x256x256)", net, synth.synth_volume((24, 1, 256, 256), 1338).cuda(),
+        synth.synth_labels((24, 256, 256), 4, 1339).cuda(), 12, 256)
+    del net
+    net = SwinUnet(swin_tiny_lite_config(), img_size=224, num_classes=4)
+    synth.load_synth(net, 4404)
+    run("config 4 (SwinUnet ICL, 16 x 1x224x224)", net, synth.synth_volume((16, 1, 224, 224), 4405).cuda(),
+        synth.synth_labels((16, 224, 224), 4, 4406).cuda(), 8, 224)
+
+
+if __name__ == "__main__":
+    main()
