@@ -8,7 +8,6 @@ import torch.nn.functional as F
 
 sys.path.insert(0, ".")
 from icl_b200.networks.unet import UNet  # noqa: E402
-from oracle import synth  # noqa: E402
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -34,8 +33,13 @@ def ref_forward(net, x):
 
 
 def run(size, B, K=4, dbl=False):
-    net = UNet(1, K)
-    synth.load_synth(net, 7)
+    torch.manual_seed(7)
+    net = UNet(1, K)  # constructor init; BatchNorm affine parameters perturbed so that gamma / beta gradients are exercised
+    with torch.no_grad():
+        for m in net.modules():
+            if isinstance(m, torch.nn.BatchNorm2d):
+                m.weight.uniform_(0.5, 1.5)
+                m.bias.uniform_(-0.3, 0.3)
     net.cuda().train()
     for m in net.modules():
         if m.__class__.__name__ == "Dropout":
@@ -43,8 +47,9 @@ def run(size, B, K=4, dbl=False):
     ref = copy.deepcopy(net)
     if dbl:
         ref = ref.double()
-    x = synth.synth_volume((B, 1, size, size), 8).cuda()
-    y = synth.synth_labels((B, size, size), K, 9).cuda()
+    g = torch.Generator().manual_seed(8)
+    x = torch.randn(B, 1, size, size, generator=g).cuda()
+    y = torch.randint(0, K, (B, size, size), generator=g).cuda()
     lr = ref_forward(ref, x.double() if dbl else x)
     (F.cross_entropy(lr, y.long())).backward()
     outs = []

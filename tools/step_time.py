@@ -9,7 +9,6 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from icl_b200.utils import losses as L  # noqa: E402
-from oracle import synth  # noqa: E402  (synthetic weights / inputs only)
 
 
 def run(name, net, x, y, n_lab, size, iters=5):
@@ -42,15 +41,15 @@ def run(name, net, x, y, n_lab, size, iters=5):
 def main():
     from icl_b200.networks.unet_icl import UNet_icl
     from icl_b200.networks.vision_transformer import SwinUnet, swin_tiny_lite_config
-    net = UNet_icl(1, 4)
-    synth.load_synth(net, 1337)
-    run("config 1 (UNet_icl, 24 x 1x256x256)", net, synth.synth_volume((24, 1, 256, 256), 1338).cuda(),
-        synth.synth_labels((24, 256, 256), 4, 1339).cuda(), 12, 256)
+    g = torch.Generator().manual_seed(1337)
+    torch.manual_seed(1337)
+    net = UNet_icl(1, 4)  # constructor init (random weights), synthetic inputs
+    run("config 1 (UNet_icl, 24 x 1x256x256)", net, torch.randn(24, 1, 256, 256, generator=g).cuda(),
+        torch.randint(0, 4, (24, 256, 256), generator=g).cuda(), 12, 256)
     del net
     net = SwinUnet(swin_tiny_lite_config(), img_size=224, num_classes=4)
-    synth.load_synth(net, 4404)
-    run("config 4 (SwinUnet ICL, 16 x 1x224x224)", net, synth.synth_volume((16, 1, 224, 224), 4405).cuda(),
-        synth.synth_labels((16, 224, 224), 4, 4406).cuda(), 8, 224)
+    run("config 4 (SwinUnet ICL, 16 x 1x224x224)", net, torch.randn(16, 1, 224, 224, generator=g).cuda(),
+        torch.randint(0, 4, (16, 224, 224), generator=g).cuda(), 8, 224)
 
 
 if __name__ == "__main__":
