@@ -32,7 +32,7 @@ def eval_dropout_only(model):
 # tests below, tolerance 1e-3 and measured ~5e-6; MaxPool winners are a second discrete choice of the same kind and are
 # held fixed too), flips are counted and bounded separately, and the comparisons with the
 # reference's fixtures keep a flip-sized tolerance on gradients while logits / losses keep the 1e-3 north-star bound.
-GRAD_FLIP_TOL = 3e-2
+GRAD_FLIP_TOL = 6e-2  # 2x the largest per-parameter difference measured in parity mode (2.8e-2, profiles/r01n_unet2d_grads_parity_vs_f64.txt)
 
 
 def _masked_leaky(pre, mask, slope=0.01):
