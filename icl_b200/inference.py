@@ -36,11 +36,15 @@ def _finalize(score, cnt):
     return label
 
 
+def _check_device(dev):
+    if dev.type != "cuda":
+        raise RuntimeError("icl_b200 inference runs on CUDA only (no CPU fallback)")
+
+
 def sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=0, world_size=1, inference_kw=False):
     """Returns (score [K,ww,hh,dd], cnt [ww,hh,dd], pads) for this rank's share of the windows."""
     dev = next(net.parameters()).device
-    if dev.type != "cuda":
-        raise RuntimeError("icl_b200 inference runs on CUDA only (no CPU fallback)")
+    _check_device(dev)
     img = torch.as_tensor(np.asarray(image), dtype=torch.float32)
     w, h, d = img.shape
     pads = []
@@ -79,6 +83,29 @@ def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1,
 
 
 test_single_case.__test__ = False  # not a pytest test
+
+
+def test_single_case_sharded(net, image, stride_xy, stride_z, patch_size, num_classes=1, group=None, inference_kw=False):
+    """Window-sharded test_single_case: every rank of the initialised process group evaluates its round-robin
+    share of the windows, the score map and the visit counts are summed with one all-reduce each (the only exchange step of the
+    path), and every rank finalises the same label map.  The sums are formed in a different order than the single-process
+    accumulation, so scores agree to fp32 rounding and the argmax can differ only where two class scores tie to ~1e-7.
+    Without an initialised process group this is test_single_case."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    w, h, d = np.asarray(image).shape
+    score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=rank, world_size=world,
+                                             inference_kw=inference_kw)
+    if world > 1:
+        dist.all_reduce(score, group=group)
+        dist.all_reduce(cnt, group=group)
+    label = _finalize(score, cnt)
+    label = label[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
+    return label.cpu().numpy()
+
+
+test_single_case_sharded.__test__ = False  # not a pytest test
 
 
 def dice_metric(pred, gt):
