@@ -68,11 +68,13 @@ class GradAverager:
         flat = torch.cat([p.grad.reshape(-1) for p in todo])
         dist.all_reduce(flat, group=self.group)
         flat.mul_(1.0 / self.world)
-        off = 0
+        views, off = [], 0
         for p in todo:
             n = p.numel()
-            p.grad.copy_(flat[off:off + n].view_as(p.grad))
+            views.append(flat[off:off + n].view_as(p.grad))
             off += n
+        # one multi-tensor copy instead of ~330 small launches (each is a node of the captured step graph)
+        torch._foreach_copy_([p.grad for p in todo], views)
         self.bytes_last = flat.numel() * 4
 
     def close(self):
