@@ -80,3 +80,13 @@ def test_state_dict_interchange_with_live_reference(monkeypatch):
     mine = unet_3D(feature_scale=4, n_classes=3, in_channels=2)
     mine.load_state_dict(ref.state_dict(), strict=True)
     ref.load_state_dict(mine.state_dict(), strict=True)
+
+
+def test_2d_and_swin_mirrors_refuse_cpu_tensors():
+    """No CPU fallback on the 2D / Swin paths either: the first kernel-backed op raises."""
+    from icl_b200.networks.unet_icl import UNet_icl
+    from icl_b200.networks.vision_transformer import SwinUnet, swin_tiny_lite_config
+    with pytest.raises(RuntimeError, match="CUDA"):
+        UNet_icl(1, 4)(torch.zeros(1, 1, 32, 32), torch.zeros(1, 1, 32, 32))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        SwinUnet(swin_tiny_lite_config(), img_size=224, num_classes=4)(torch.zeros(1, 1, 224, 224), inference=True)
