@@ -34,13 +34,17 @@ _CT = {
 }
 
 
+_RET = {}
+
+
 def header_prototypes():
     """Parse include/icl_b200.h -> {name: [(ctype, argname), ...]} (pointers map to c_void_p)."""
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
     protos = {}
-    for m in re.finditer(r"\b(int|unsigned long long|const char\*)\s+(icl_\w+)\s*\(([^)]*)\)\s*;", txt):
+    for m in re.finditer(r"\b(unsigned long long|long long|int|const char\*)\s+(icl_\w+)\s*\(([^)]*)\)\s*;", txt):
         name, args = m.group(2), m.group(3).strip()
+        _RET[name] = m.group(1)
         sig = []
         if args and args != "void":
             for a in args.split(","):
@@ -59,7 +63,7 @@ def _declare(l):
         fn = getattr(l, name)
         fn.argtypes = [t for t, _ in sig]
         if name not in ("icl_last_error", "icl_launch_count"):
-            fn.restype = ctypes.c_int
+            fn.restype = ctypes.c_longlong if _RET.get(name) == "long long" else ctypes.c_int
 
 
 def ptr(t):

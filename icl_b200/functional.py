@@ -45,9 +45,9 @@ class LinearFn(torch.autograd.Function):
                 # dy^T x inside the momentum-SGD update; the 764 MB gradient tensor is never materialised (.grad stays None)
                 if dp["world"] > 1:
                     gd, xd = parallel.gather_factors(g, x2, dp["group"])
-                    sink.append((gd * (1.0 / dp["world"]), xd))
+                    sink.append((gd, xd, 1.0 / dp["world"]))
                 else:
-                    sink.append((g, x2))
+                    sink.append((g, x2, 1.0))
                 if ctx.has_bias:
                     db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
                     call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))

@@ -263,13 +263,31 @@ def sgemm(M, N, K, A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias=None, bias_mode=
          gflop=2e-9 * M * N * K * batch, mbytes=4e-6 * batch * (M * K + K * N + M * N), tag="%dx%dx%d b%d" % (M, N, K, batch))
 
 
+BIGW_MIN_NUMEL = 1 << 22  # weights at least this large stream through the tcgen05 kernels (bigw_umma.cu)
+
+
+def bigw_ok(M, N, K):
+    """Linear shapes the tcgen05 weight-streaming kernels take: a big weight, few rows (ICL_DISABLE_BIGW=1 turns them off)."""
+    if os.environ.get("ICL_DISABLE_BIGW") == "1" or not tensor_cores():
+        return False
+    return N * K >= BIGW_MIN_NUMEL and M <= 512 and K % 4 == 0 and N % 4 == 0
+
+
+def _bigw_ws(rows, M, K, device):
+    return torch.empty((int(_lib.lib().icl_bigw_workspace(rows, M, K)),), dtype=torch.uint8, device=device)
+
+
 def linear_fwd(x2d, w, b, act=0, want_pre=False):
     """y = act(x2d @ w.T + b); x2d [M,K] contiguous, w [N,K]."""
     M, K = x2d.shape
     N = w.shape[0]
     y = torch.empty((M, N), dtype=torch.float32, device=x2d.device)
     pre = torch.empty_like(y) if want_pre else None
-    if M <= 64 and K >= 1024 and K % 4 == 0:
+    if bigw_ok(M, N, K):
+        ws = _bigw_ws(M, N, K, x2d.device)
+        call("icl_bigw_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act), P(ws),
+             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
+    elif M <= 64 and K >= 1024 and K % 4 == 0:
         call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act),
              mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
     else:
@@ -280,6 +298,12 @@ def linear_fwd(x2d, w, b, act=0, want_pre=False):
 def linear_dgrad(dy2d, w):
     M, N = dy2d.shape
     K = w.shape[1]
+    if bigw_ok(M, N, K):
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy2d.device)
+        ws = _bigw_ws(M, K, N, dy2d.device)
+        call("icl_bigw_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), P(ws), mbytes=4e-6 * (N * K + M * K + M * N),
+             gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
+        return dx
     if M <= 64 and N >= 1024 and K % 4 == 0:
         dx = torch.zeros((M, K), dtype=torch.float32, device=dy2d.device)
         call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), mbytes=4e-6 * (N * K + M * K + M * N),
@@ -332,3 +356,23 @@ def row_combine(a, sa, b, sb, rows):
     out = torch.empty_like(a)
     call("icl_row_combine", P(a), P(sa), P(b), P(sb), P(out), c_ll(rows), c_ll(a.numel() // rows))
     return out
+
+
+def sgd_factored(p, m, factors, lr, mu, wd):
+    """Momentum-SGD update of a huge 2-D weight from its rank-R gradient factors [(dy [r,N], x [r,K], scale), ...]:
+    g = sum dy^T x (+ wd p), m = mu m + g, p -= lr m.  tcgen05 path when the shape allows, CUDA-core kernel otherwise."""
+    N, K = p.shape
+    R = sum(f[0].shape[0] for f in factors)
+    if tensor_cores() and N % 8 == 0 and K % 8 == 0 and os.environ.get("ICL_DISABLE_BIGW") != "1":
+        ws = torch.empty((int(_lib.lib().icl_sgd_factored_workspace(R, N, K)),), dtype=torch.uint8, device=p.device)
+        r0 = 0
+        for dy, x, scale in factors:
+            call("icl_sgd_factored_pack", P(dy), P(x), c_int(dy.shape[0]), c_int(r0), c_int(R), c_int(N), c_int(K), c_f(scale), P(ws))
+            r0 += dy.shape[0]
+        call("icl_sgd_factored_apply", c_int(R), c_int(N), c_int(K), P(ws), P(p), P(m), P(lr), c_f(mu), c_f(wd), c_int(_MAX_CTAS),
+             mbytes=16e-6 * p.numel(), gflop=2e-9 * R * N * K, tag="R%d %dx%d" % (R, N, K))
+    else:
+        dy = torch.cat([f[0] * f[2] if f[2] != 1.0 else f[0] for f in factors], 0).contiguous()
+        x = torch.cat([f[1] for f in factors], 0).contiguous()
+        call("icl_sgd_factored", c_int(R), c_int(N), c_int(K), P(dy), P(x), P(p), P(m), P(lr), c_f(mu), c_f(wd),
+             mbytes=16e-6 * p.numel(), tag="R%d %dx%d" % (R, N, K))

@@ -8,7 +8,7 @@ entirely (no weight decay, no momentum) exactly like torch.  One kernel launch p
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, ops
 from .ops import P, c_f, c_int, call
 
 
@@ -60,14 +60,11 @@ class SGD(torch.optim.Optimizer):
                 continue
             if p.grad is not None:
                 raise RuntimeError("icl_b200.optim.SGD: a fused-factored weight also has a materialised .grad")
-            dy = torch.cat([f[0] for f in fs], 0).contiguous()
-            x = torch.cat([f[1] for f in fs], 0).contiguous()
             st = self.state[p]
             if "momentum_buffer" not in st:
                 st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
-            N, K = p.shape
-            call("icl_sgd_factored", c_int(dy.shape[0]), c_int(N), c_int(K), P(dy), P(x), P(p), P(st["momentum_buffer"]), P(lr),
-                 c_f(group["momentum"]), c_f(group["weight_decay"]), mbytes=16e-6 * p.numel(), tag="R%d %dx%d" % (dy.shape[0], N, K))
+            ops.sgd_factored(p, st["momentum_buffer"], [(f[0], f[1], f[2] if len(f) > 2 else 1.0) for f in fs], lr, group["momentum"],
+                             group["weight_decay"])
             fs.clear()
 
     def _lr_tensor(self, gi, group, dev):

@@ -112,6 +112,13 @@ int icl_sgemm(int M, int N, int K, const float* A, long long sam, long long sak,
 int icl_skinny_linear_fwd(int M, int N, int K, const float* x, const float* Wt, const float* bias, float* y, float* pre, int act, void* stream);
 int icl_skinny_linear_dgrad(int M, int N, int K, const float* dy, const float* Wt, float* dx, void* stream);
 int icl_outer_wgrad(int M, int N, int K, const float* dy, const float* x, float* dW, float* db, int accumulate, void* stream);
+/* the same Linears on the 5th-gen tensor cores (tcgen05 / TMEM / TMA, split-bf16 x3): the fp32 weight is streamed once by TMA,
+ * converted to bf16 hi/lo into TMEM (A operand), any number of rows (128 per weight pass); `workspace` = device buffer of
+ * icl_bigw_workspace(rows, out_features, in_features) bytes (dgrad: (rows, in_features, out_features)) */
+long long icl_bigw_workspace(int rows, int M, int K);
+int icl_bigw_linear_fwd(int rows, int N, int K, const float* x, const float* W, const float* bias, float* y, float* pre, int act, void* workspace,
+                        void* stream);
+int icl_bigw_linear_dgrad(int rows, int N, int K, const float* dy, const float* W, float* dx, void* workspace, void* stream);
 int icl_colsum(const float* a, float* out, long long M, int N, int accumulate, void* stream);
 int icl_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream);
 
@@ -160,6 +167,14 @@ int icl_sgd_chunk(void);
 /* fused rank-R weight gradient + SGD update for the mlp2 weights: the gradient dy^T x is formed on the fly, never stored */
 int icl_sgd_factored(int R, int N, int K, const float* dy, const float* x, float* p, float* m, const float* lr_ptr, float mu, float wd,
                      void* stream);
+
+/* the same update on the tensor cores: factor pairs are packed (split bf16) into a workspace of icl_sgd_factored_workspace bytes with
+ * one icl_sgd_factored_pack per (dy [rows][N], x [rows][K]) pair (dy scaled by `scale`, e.g. 1/world), then one
+ * icl_sgd_factored_apply forms dy^T x in TMEM and streams p, m through TMA tiles (16 B of HBM traffic per parameter for any R) */
+long long icl_sgd_factored_workspace(int R, int N, int K);
+int icl_sgd_factored_pack(const float* dy, const float* x, int rows, int r0, int R_total, int N, int K, float scale, void* workspace, void* stream);
+int icl_sgd_factored_apply(int R_total, int N, int K, const void* workspace, float* p, float* m, const float* lr_ptr, float mu, float wd,
+                           int max_ctas, void* stream);
 
 /* ---- sliding-window inference + Dice counts: test_3D_BraTS.py:110-135,175-187 (val_3D.py:43-97) ---- */
 int icl_sw_accumulate(const float* logits, int K, int pw, int ph, int pd, float* score, float* cnt, int W, int H, int D, int xs, int ys, int zs,

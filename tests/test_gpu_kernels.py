@@ -634,3 +634,60 @@ def test_sliding_window_kernels_and_dice_counts():
     rd, rc = R.dice_metric(pred.numpy(), gt.numpy())
     assert counts == rc and dice == rd
     assert inference.dice_metric(torch.zeros(4, 4, 4, dtype=torch.long).cuda(), torch.zeros(4, 4, 4, dtype=torch.long).cuda())[0] == 1.0
+
+
+# ------------------------------------------------------------------------------------------ tcgen05 weight-streaming GEMMs
+@pytest.mark.parametrize("M,N,K", [(16, 256, 128), (16, 4100, 2052), (48, 1000, 4224), (128, 4224, 4100), (100, 13824, 2048), (200, 1100, 1028),
+                                   (300, 640, 512)])
+def test_bigw_linear_abi(M, N, K):
+    """icl_bigw_linear_{fwd,dgrad} straight through the C-ABI (tcgen05, W converted fp32 -> split bf16 into TMEM): edge tiles in the
+    output axis, a reduction tail (K % 32 != 0), row padding (M % 16 != 0) and more than one 128-row pass."""
+    from icl_b200 import _lib
+    from icl_b200.ops import P, c_int, call
+    x = torch.randn(M, K, generator=g(1)).cuda()
+    w = (torch.randn(N, K, generator=g(2)) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g(3)).cuda()
+    lib = _lib.lib()
+    for act in (0, 1):
+        y = torch.empty(M, N, device="cuda")
+        pre = torch.empty(M, N, device="cuda")
+        ws = torch.empty(int(lib.icl_bigw_workspace(M, N, K)), dtype=torch.uint8, device="cuda")
+        call("icl_bigw_linear_fwd", c_int(M), c_int(N), c_int(K), P(x), P(w), P(b), P(y), P(pre), c_int(act), P(ws))
+        ref = F.linear(x.double(), w.double(), b.double())
+        assert_close(pre.cpu(), ref.cpu(), 2e-5, "bigw fwd pre-activation")
+        assert_close(y.cpu(), (F.gelu(ref) if act else ref).cpu(), 2e-5, "bigw fwd act=%d" % act)
+    dy = torch.randn(M, N, generator=g(4)).cuda()
+    dx = torch.empty(M, K, device="cuda")
+    ws = torch.empty(int(lib.icl_bigw_workspace(M, K, N)), dtype=torch.uint8, device="cuda")
+    call("icl_bigw_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy), P(w), P(dx), P(ws))
+    assert_close(dx.cpu(), (dy.double() @ w.double()).cpu(), 2e-5, "bigw dgrad")
+
+
+@pytest.mark.parametrize("R1,R2,N,K,ctas", [(16, 0, 256, 512, 0), (9, 12, 1000, 776, 3), (128, 128, 2048, 1024, 0), (40, 300, 392, 264, 0)])
+def test_sgd_factored_umma_abi(R1, R2, N, K, ctas):
+    """icl_sgd_factored_pack / _apply through the C-ABI against torch.optim.SGD on the materialised gradient: two factor pairs (one
+    scaled), ragged R, edge tiles in both weight axes, the persistent tile loop (ctas = 3), three steps (momentum)."""
+    from icl_b200 import _lib
+    from icl_b200.ops import P, c_f, c_int, call
+    lib = _lib.lib()
+    p0 = torch.randn(N, K, generator=g(1)) * 0.3
+    ref = p0.clone().double().requires_grad_(True)
+    o_ref = torch.optim.SGD([ref], lr=0.05, momentum=0.9, weight_decay=1e-2)
+    p = p0.clone().cuda()
+    m = torch.zeros_like(p)
+    lr = torch.tensor([0.05], device="cuda")
+    for step in range(3):
+        pairs = [(torch.randn(R1, N, generator=g(10 + step)), torch.randn(R1, K, generator=g(20 + step)), 1.0)]
+        if R2:
+            pairs.append((torch.randn(R2, N, generator=g(30 + step)), torch.randn(R2, K, generator=g(40 + step)), 0.5))
+        ref.grad = sum(s * (dy.double().t() @ x.double()) for dy, x, s in pairs)
+        o_ref.step()
+        R = R1 + R2
+        ws = torch.empty(int(lib.icl_sgd_factored_workspace(R, N, K)), dtype=torch.uint8, device="cuda")
+        r0 = 0
+        for dy, x, s in pairs:
+            dyc, xc = dy.cuda(), x.cuda()
+            call("icl_sgd_factored_pack", P(dyc), P(xc), c_int(dy.shape[0]), c_int(r0), c_int(R), c_int(N), c_int(K), c_f(s), P(ws))
+            r0 += dy.shape[0]
+        call("icl_sgd_factored_apply", c_int(R), c_int(N), c_int(K), P(ws), P(p), P(m), P(lr), c_f(0.9), c_f(1e-2), c_int(ctas))
+    assert_close(p.cpu(), ref.detach().float(), 2e-5, "sgd_factored_umma param")

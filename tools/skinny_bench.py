@@ -32,23 +32,35 @@ def main():
     peak = json.load(open(pk)).get("hbm_gbs", 6546.2) if os.path.exists(pk) else 6546.2
     only = sys.argv[1] if len(sys.argv) > 1 else ""
     g = torch.Generator(device="cuda").manual_seed(1)
-    for rows, n in ((16, 13824), (128, 13824), (32, 1728), (64, 216)):
+    for rows, n in ((16, 13824), (128, 13824), (32, 1728), (256, 1728)):
         x = torch.randn(rows, n, device="cuda", generator=g)
         w = torch.randn(n, n, device="cuda", generator=g) * 0.01
         b = torch.zeros(n, device="cuda")
         mb = n * n * 4 / 1e6
-        if only in ("", "fwd"):
-            ms = timeit(lambda: ops.linear_fwd(x, w, b, 1, want_pre=True))
-            print("linear_fwd  %4dx%dx%d  %8.3f ms  %7.0f GB/s (%4.1f%% of %.0f)" % (rows, n, n, ms, mb / ms, 100 * mb / ms / peak, peak), flush=True)
-        if only in ("", "dgrad"):
-            ms = timeit(lambda: ops.linear_dgrad(x, w))
-            print("linear_dgrad %4dx%dx%d %8.3f ms  %7.0f GB/s (%4.1f%%)" % (rows, n, n, ms, mb / ms, 100 * mb / ms / peak), flush=True)
-        if only in ("", "sgd") and rows == 16:
+        for mode in ("umma", "legacy"):
+            os.environ["ICL_DISABLE_BIGW"] = "0" if mode == "umma" else "1"
+            if only in ("", "fwd"):
+                ms = timeit(lambda: ops.linear_fwd(x, w, b, 1, want_pre=True))
+                print("%-6s linear_fwd   %4dx%dx%d  %8.3f ms  %7.0f GB/s (%4.1f%% of %.0f)  %6.1f TFLOP/s" % (
+                    mode, rows, n, n, ms, mb / ms, 100 * mb / ms / peak, peak, 2e-9 * rows * n * n / ms), flush=True)
+            if only in ("", "dgrad"):
+                ms = timeit(lambda: ops.linear_dgrad(x, w))
+                print("%-6s linear_dgrad %4dx%dx%d  %8.3f ms  %7.0f GB/s (%4.1f%%)" % (mode, rows, n, n, ms, mb / ms, 100 * mb / ms / peak), flush=True)
+        os.environ["ICL_DISABLE_BIGW"] = "0"
+        if only in ("", "sgd") and n == 13824 and rows == 16:
             m = torch.zeros_like(w)
             lr = torch.full((1,), 0.01, device="cuda")
-            dy = torch.randn(rows, n, device="cuda", generator=g)
-            ms = timeit(lambda: call("icl_sgd_factored", c_int(rows), c_int(n), c_int(n), P(dy), P(x), P(w), P(m), P(lr), c_f(0.9), c_f(1e-4)))
-            print("sgd_factored R%d %dx%d      %8.3f ms  %7.0f GB/s of 16 B/param (%4.1f%%)" % (rows, n, n, ms, 4 * mb / ms, 100 * 4 * mb / ms / peak), flush=True)
+            for R in (32, 64, 256, 512, 1024, 2048):
+                dy = torch.randn(R, n, device="cuda", generator=g) * 0.01
+                xx = torch.randn(R, n, device="cuda", generator=g)
+                for mode in ("umma", "legacy"):
+                    if mode == "legacy" and R > 256:
+                        continue
+                    os.environ["ICL_DISABLE_BIGW"] = "0" if mode == "umma" else "1"
+                    ms = timeit(lambda: ops.sgd_factored(w, m, [(dy, xx, 1.0)], lr, 0.9, 1e-4), iters=4)
+                    print("%-6s sgd_factored R%-4d %dx%d  %8.3f ms  %7.0f GB/s of 16 B/param (%4.1f%%)  %6.1f TFLOP/s" % (
+                        mode, R, n, n, ms, 4 * mb / ms, 100 * 4 * mb / ms / peak, 2e-9 * R * n * n / ms), flush=True)
+            os.environ["ICL_DISABLE_BIGW"] = "0"
 
 
 if __name__ == "__main__":
