@@ -44,10 +44,12 @@ class LinearFn(torch.autograd.Function):
                 # fused optimizer path: hand the rank-<=rows factors to the optimizer, which forms
                 # dy^T x inside the momentum-SGD update; the 764 MB gradient tensor is never materialised (.grad stays None)
                 if dp["world"] > 1:
-                    gd, xd = parallel.gather_factors(g, x2, dp["group"])
-                    sink.append((gd, xd, 1.0 / dp["world"]))
+                    # the factors are ready at the very start of backward: gather them on the exchange stream while the rest of
+                    # backward runs; the optimizer waits on the event before it packs them
+                    gd, xd, ev, keep = parallel.gather_factors_async(g, x2, dp["group"])
+                    sink.append((gd, xd, 1.0 / dp["world"], ev, keep))
                 else:
-                    sink.append((g, x2, 1.0))
+                    sink.append((g, x2, 1.0, None, None))
                 if ctx.has_bias:
                     db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
                     call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))

@@ -36,3 +36,13 @@ class GraphedStep:
             self.optimizer.sync_lr()
         self.graph.replay()
         return self.static_out
+
+    def release(self):
+        """Drop the captured graph (and the NCCL work it holds).  Call before torch.distributed.destroy_process_group():
+        tearing the communicator down while a live graph still references its collectives hangs."""
+        torch.cuda.synchronize()
+        if self.graph is not None:
+            self.graph.reset()
+        self.graph = None
+        self.static_out = None
+        torch.cuda.synchronize()

@@ -41,42 +41,45 @@ def _check_device(dev):
         raise RuntimeError("icl_b200 inference runs on CUDA only (no CPU fallback)")
 
 
-def sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=0, world_size=1, inference_kw=False):
-    """Returns (score [K,ww,hh,dd], cnt [ww,hh,dd], pads) for this rank's share of the windows."""
+def sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=0, world_size=1, inference_kw=False, window_batch=1):
+    """Returns (score [K,ww,hh,dd], cnt [ww,hh,dd], pads) for this rank's share of the windows.  `image`: numpy / CPU tensor
+    [w,h,d] (copied to the device once) or a tensor already on the device.  `window_batch` windows go through the network per
+    call (the reference runs one, test_3D_BraTS.py:119-133); the per-voxel accumulation order (x, then y, then z) is unchanged."""
     dev = next(net.parameters()).device
     _check_device(dev)
-    img = torch.as_tensor(np.asarray(image), dtype=torch.float32)
+    img = image if isinstance(image, torch.Tensor) else torch.as_tensor(np.asarray(image), dtype=torch.float32)
+    img = img.to(device=dev, dtype=torch.float32, non_blocking=True)
     w, h, d = img.shape
     pads = []
     for s, p in zip((w, h, d), patch_size):
         tot = max(p - s, 0)
         pads.append((tot // 2, tot - tot // 2))
-    img = img.to(dev, non_blocking=True)
     if any(a + b > 0 for a, b in pads):
         img = torch.nn.functional.pad(img, (pads[2][0], pads[2][1], pads[1][0], pads[1][1], pads[0][0], pads[0][1]))
     ww, hh, dd = img.shape
     px, py, pz = patch_size
     score = torch.zeros((num_classes, ww, hh, dd), dtype=torch.float32, device=dev)
     cnt = torch.zeros((ww, hh, dd), dtype=torch.float32, device=dev)
-    n = 0
+    wins = [(xs, ys, zs) for xs in window_starts(ww, px, stride_xy) for ys in window_starts(hh, py, stride_xy)
+            for zs in window_starts(dd, pz, stride_z)]
+    mine = [wn for n, wn in enumerate(wins) if (n % world_size) == rank]
+    nb = max(1, int(window_batch))
     with torch.no_grad():
-        for xs in window_starts(ww, px, stride_xy):
-            for ys in window_starts(hh, py, stride_xy):
-                for zs in window_starts(dd, pz, stride_z):
-                    mine = (n % world_size) == rank
-                    n += 1
-                    if not mine:
-                        continue
-                    patch = img[xs:xs + px, ys:ys + py, zs:zs + pz].contiguous()[None, None]
-                    y1 = net(patch, inference=True) if inference_kw else net(patch)
-                    _accumulate(ops.to_ndhwc(y1)[0], score, cnt, xs, ys, zs)
+        for i in range(0, len(mine), nb):
+            grp = mine[i:i + nb]
+            patch = torch.stack([img[xs:xs + px, ys:ys + py, zs:zs + pz] for xs, ys, zs in grp])[:, None]
+            y1 = net(patch, inference=True) if inference_kw else net(patch)
+            y1 = ops.to_ndhwc(y1)
+            for j, (xs, ys, zs) in enumerate(grp):
+                _accumulate(y1[j], score, cnt, xs, ys, zs)
     return score, cnt, pads
 
 
-def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, inference_kw=False):
+def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, inference_kw=False, window_batch=1):
     """numpy [w,h,d] in -> numpy int64 label map out (host-blocking, like the reference)."""
-    w, h, d = np.asarray(image).shape
-    score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, inference_kw=inference_kw)
+    w, h, d = image.shape
+    score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, inference_kw=inference_kw,
+                                             window_batch=window_batch)
     label = _finalize(score, cnt)
     label = label[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
     return label.cpu().numpy()
@@ -85,7 +88,7 @@ def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1,
 test_single_case.__test__ = False  # not a pytest test
 
 
-def test_single_case_sharded(net, image, stride_xy, stride_z, patch_size, num_classes=1, group=None, inference_kw=False):
+def test_single_case_sharded(net, image, stride_xy, stride_z, patch_size, num_classes=1, group=None, inference_kw=False, window_batch=1):
     """Window-sharded test_single_case: every rank of the initialised process group evaluates its round-robin
     share of the windows, the score map and the visit counts are summed with one all-reduce each (the only exchange step of the
     path), and every rank finalises the same label map.  The sums are formed in a different order than the single-process
@@ -94,9 +97,9 @@ def test_single_case_sharded(net, image, stride_xy, stride_z, patch_size, num_cl
     import torch.distributed as dist
     on = dist.is_available() and dist.is_initialized()
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
-    w, h, d = np.asarray(image).shape
+    w, h, d = image.shape
     score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=rank, world_size=world,
-                                             inference_kw=inference_kw)
+                                             inference_kw=inference_kw, window_batch=window_batch)
     if world > 1:
         dist.all_reduce(score, group=group)
         dist.all_reduce(cnt, group=group)

@@ -45,7 +45,7 @@ class SGD(torch.optim.Optimizer):
             ct = torch.from_numpy(np.concatenate(ct)).to(device)
             co = torch.from_numpy(np.concatenate(co)).to(device)
             hit = (ct, co)
-            self._cache = {key: hit}
+            self._cache[key] = hit
         return hit
 
     def zero_grad(self, set_to_none=True):
@@ -63,6 +63,9 @@ class SGD(torch.optim.Optimizer):
             st = self.state[p]
             if "momentum_buffer" not in st:
                 st["momentum_buffer"] = torch.zeros_like(p, memory_format=torch.contiguous_format)
+            for f in fs:
+                if len(f) > 3 and f[3] is not None:
+                    torch.cuda.current_stream().wait_event(f[3])   # factors all-gathered on the exchange stream (icl_b200.parallel)
             ops.sgd_factored(p, st["momentum_buffer"], [(f[0], f[1], f[2] if len(f) > 2 else 1.0) for f in fs], lr, group["momentum"],
                              group["weight_decay"])
             fs.clear()
@@ -91,8 +94,11 @@ class SGD(torch.optim.Optimizer):
         spare pinned/device pair is kept ready because pinned memory cannot be allocated during stream capture."""
         key = tuple(rows)
         cache = self._tab_cache.setdefault(gi, {"tabs": {}, "spare": None})
-        hit = cache["tabs"].get(key)
+        captured = cache.setdefault("captured", {})
+        hit = captured.get(key) or cache["tabs"].get(key)
         capturing = torch.cuda.is_current_stream_capturing()
+        if hit is not None and capturing:
+            captured[key] = hit
         if hit is None:
             shape = (len(rows), 4)
             sp = cache["spare"]
@@ -106,9 +112,13 @@ class SGD(torch.optim.Optimizer):
                 tab = torch.empty(shape, dtype=torch.int64, device=dev)
             host.numpy()[...] = np.asarray(rows, dtype=np.int64)
             tab.copy_(host, non_blocking=True)
-            if len(cache["tabs"]) >= 8:
-                cache["tabs"].pop(next(iter(cache["tabs"])))
-            hit = cache["tabs"][key] = (host, tab)
+            if capturing:
+                # a captured graph replays this upload for as long as it lives: its table is never evicted
+                hit = cache["captured"][key] = (host, tab)
+            else:
+                if len(cache["tabs"]) >= 8:
+                    cache["tabs"].pop(next(iter(cache["tabs"])))
+                hit = cache["tabs"][key] = (host, tab)
         if cache["spare"] is None and not capturing:
             shape = (len(rows), 4)
             cache["spare"] = (torch.empty(shape, dtype=torch.int64).pin_memory(), torch.empty(shape, dtype=torch.int64, device=dev))

@@ -35,6 +35,20 @@ def summarize(t, n=64):
     return np.array([t.sum().item(), t.norm().item()], dtype=np.float64), t[idx].float().numpy()
 
 
+def pack_labels(labels, K):
+    """Label map (ints < K) -> bit planes packed with np.packbits: uint8 [nbits, ceil(numel / 8)] (per-voxel argmax parity)."""
+    a = np.asarray(labels).reshape(-1).astype(np.uint8)
+    nbits = max(1, int(np.ceil(np.log2(K))))
+    return np.stack([np.packbits((a >> b) & 1) for b in range(nbits)])
+
+
+def unpack_labels(packed, numel):
+    out = np.zeros(numel, dtype=np.int64)
+    for b in range(packed.shape[0]):
+        out |= np.unpackbits(packed[b])[:numel].astype(np.int64) << b
+    return out
+
+
 def eval_dropout_only(model):
     """Dropout / DropPath -> identity; BatchNorm stays in train mode."""
     for m in model.modules():
@@ -153,6 +167,7 @@ def gen_step(ns, K, name, weights):
         s, v = summarize(t, 4096)
         out[nm + "_sum"], out[nm + "_val"] = s, v
         out[nm + "_argmax_count"] = np.bincount(t.argmax(1).reshape(-1).numpy(), minlength=K)
+        out[nm + "_argmax_bits"] = pack_labels(t.argmax(1).numpy(), K)
     for j, nm in ((2, "maps_lab"), (3, "maps_unlab"), (4, "maps_consis")):
         for i in range(3):
             t = o[j][i].detach()
@@ -278,6 +293,7 @@ def gen_step2d(ns):
         sm, v = summarize(t, 4096)
         out[nm + "_sum"], out[nm + "_val"] = sm, v
         out[nm + "_argmax_count"] = np.bincount(t.argmax(1).reshape(-1).numpy(), minlength=K)
+        out[nm + "_argmax_bits"] = pack_labels(t.argmax(1).numpy(), K)
     for j, nm in ((2, "maps_lab"), (3, "maps_unlab"), (4, "maps_consis")):
         for i in range(3):
             sm, v = summarize(o[j][i].detach(), 4096)
@@ -330,6 +346,7 @@ def gen_step_swin(ns, name, n_lab, n_unlab, seed):
         sm, v = summarize(t.detach(), 4096)
         out[nm + "_sum"], out[nm + "_val"] = sm, v
         out[nm + "_argmax_count"] = np.bincount(t.argmax(1).reshape(-1).numpy(), minlength=K)
+        out[nm + "_argmax_bits"] = pack_labels(t.argmax(1).numpy(), K)
     for j, nm in ((2, "maps_lab"), (3, "maps_unlab"), (4, "maps_consis")):
         for i in range(3):
             sm, v = summarize(o[j][i].detach(), 4096)

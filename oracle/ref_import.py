@@ -10,7 +10,12 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("ICL_REFERENCE_ROOT", "/root/reference")
+# /root/reference exists in the build container only; baseline/_ref (git-ignored, shipped by gpurun) is a verbatim copy of the
+# reference's code/{networks,utils} + the two eval scripts, made by __graft_entry__.build() so that the reference arm of bench.py
+# can run the UNMODIFIED reference on the GPU box too.
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.environ.get("ICL_REFERENCE_ROOT", "/root/reference"), os.path.join(_REPO, "baseline", "_ref")]
+REF_ROOT = next((r for r in _CANDIDATES if os.path.isdir(os.path.join(r, "code", "networks"))), _CANDIDATES[0])
 REF_CODE = os.path.join(REF_ROOT, "code")
 STUBS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "stubs")
 

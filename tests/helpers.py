@@ -4,7 +4,7 @@ import os
 import numpy as np
 import torch
 
-from oracle.make_golden import sample_idx  # same seeded sample positions as the fixtures
+from oracle.make_golden import sample_idx, unpack_labels  # same seeded sample positions / label packing as the fixtures
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -41,3 +41,13 @@ def check_summary(t, gsum, gval, rel, what, n=64, abs_floor=1e-7):
     err = (got - want).abs().max().item()
     assert err <= 30 * rel * rms + rel * want.abs().max().item() + abs_floor, \
         "%s: sampled max err %.3e (rms %.3e)" % (what, err, rms)
+
+
+def assert_argmax_agrees(logits, packed_bits, what, min_agree=0.999):
+    """Per-voxel agreement of argmax(logits, dim 1) with the reference's label map stored as packed bit planes in the fixture
+    (north star: label maps agree on at least 99.9 % of voxels)."""
+    got = logits.detach().argmax(1).reshape(-1).cpu().numpy()
+    want = unpack_labels(np.asarray(packed_bits), got.size)
+    agree = float((got == want).mean())
+    assert agree >= min_agree, "%s: argmax agrees on %.5f of %d voxels (need %.4f)" % (what, agree, got.size, min_agree)
+    return agree

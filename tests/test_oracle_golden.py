@@ -165,3 +165,43 @@ def test_sliding_window_golden():
     dice, counts = R.dice_metric(want, gt)
     assert list(counts) == [int(v) for v in g["counts"]]
     assert dice == float(g["dice"])
+
+
+@pytest.mark.parametrize("name", ["step_cfg2", "step_cfg3"])
+def test_train_step_port_golden(name):
+    """R.train_step_3d (the step bench.py's CPU arm times when no reference tree is reachable, kind "port") against the fixture the
+    UNMODIFIED reference produced for the same full-size step: the five losses, per-voxel label maps, the grad-is-None set and every
+    parameter gradient (785 M parameters, summarised)."""
+    import json
+    import os
+    from collections import OrderedDict
+    from helpers import GOLDEN, assert_argmax_agrees, check_summary
+    g = golden(name)
+    K = int(g["K"])
+    keys = json.load(open(os.path.join(GOLDEN, "state_keys.json")))["unet_3D_icl_k2"]
+    shapes = OrderedDict()
+    for k, s in keys:
+        s = list(s)
+        if k in ("final.weight", "final.bias"):
+            s[0] = K
+        elif k.endswith("guided_Q"):
+            s[1] = K
+        shapes[k] = tuple(s)
+    P = R.make_params(synth.synth_state_dict(shapes, 1337))
+    x = synth.synth_volume((4, 1, 96, 96, 96), 1338)
+    y = synth.synth_labels((4, 96, 96, 96), K, 1339)
+    L, grads, outputs = R.train_step_3d(P, x, y, 2, K, weights=dict(zip(("dice", "ce", "aux", "pse", "cons"), (float(v) for v in g["weights"]))),
+                                       rand=R.NoRand())
+    for k in ("ce", "dice", "aux", "pse", "cons", "total"):
+        assert abs(float(L[k]) - float(g[k])) <= 1e-5 * max(1.0, abs(float(g[k]))), (k, float(L[k]), float(g[k]))
+    assert_argmax_agrees(outputs[0], g["final_lab_argmax_bits"], "final_lab", 0.9999)
+    assert_argmax_agrees(outputs[1], g["final_unlab_argmax_bits"], "final_unlab", 0.9999)
+    none = set(str(s) for s in g["grad_none"])
+    assert set(k for k, v in grads.items() if v is None) == none
+    for k, v in grads.items():
+        if v is None:
+            continue
+        if k.endswith(".0.bias") and "sspa" not in k and "uscl" not in k:
+            assert v.norm().item() < 1e-3, k   # conv bias in front of InstanceNorm: mathematically zero gradient
+            continue
+        check_summary(v, g["gsum/" + k], g["gval/" + k], 2e-4, k, abs_floor=1e-6)
