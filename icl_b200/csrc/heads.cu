@@ -298,29 +298,77 @@ ICL_API int icl_dwconv3d(const float* x, const float* w, float* y, int NB, int C
   dwconv3d_k<<<grid_for((long long)NB * CH * d * h * wd, 256), 256, 0, as_stream(stream)>>>(x, w, y, NB, CH, d, h, wd, flip);
   ICL_LAUNCHED("dwconv3d");
 }
-// dw[c][t] = sum_{nb, v} x[nb,c,v+t-1] * dy[nb,c,v]; one block per (c, t)
-__global__ void __launch_bounds__(256) dwconv3d_wgrad_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
-                                                        int NB, int CH, int d, int h, int wd) {
-  __shared__ float red[33];
-  const int c = blockIdx.x / 27, t = blockIdx.x % 27;
-  const int oz = t / 9 - 1, oy = (t / 3) % 3 - 1, ox = t % 3 - 1;
-  const long long S = (long long)d * h * wd;
-  float s = 0.f;
-  for (long long i = threadIdx.x; i < (long long)NB * S; i += blockDim.x) {
-    const long long nb = i / S; long long v = i % S;
+// ------------------------------------------------------------------------------------------
+// Reductions over all (sample, voxel) positions of a planar [NB, CH, S] map.  At K = 16 classes the ICL heads run on
+// NB = B*K = 32 maps, so "one block per channel" (CH = 4 ... 16 blocks on 148 SMs) is latency-bound by two orders of
+// magnitude: the position axis is cut into up to RED_CHUNKS chunks (grid = chunks x channels), every block writes its
+// partial sums to a workspace and a small second kernel adds the partials in a fixed order (deterministic).
+// `ws` arguments: device scratch of at least ICL_RED_WS_BYTES bytes (icl_reduce_workspace_bytes()).
+// ------------------------------------------------------------------------------------------
+#define RED_CHUNKS 296
+#define RED_WS_BYTES (RED_CHUNKS * 16 * 32 * 8)
+ICL_API int icl_reduce_workspace_bytes(void) { return RED_WS_BYTES; }
+
+static inline int red_chunks(long long n, int per_chunk_min) {
+  long long c = (n + per_chunk_min - 1) / per_chunk_min;
+  if (c < 1) c = 1;
+  if (c > RED_CHUNKS) c = RED_CHUNKS;
+  return (int)c;
+}
+
+// dw[c][t] = sum_{nb, v} x[nb,c,v+t-1] * dy[nb,c,v].  Block = (chunk of positions, channel); a thread keeps the 27 tap sums of its
+// positions in registers (dy read once, the 27 x neighbours from L1), then warp / block reduction -> partial[c][chunk][27].
+__global__ void __launch_bounds__(256) dwconv3d_wgrad_partial_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part,
+                                                                int NB, int CH, int d, int h, int wd, int chunks) {
+  __shared__ float red[8][27];
+  const int c = blockIdx.y, chunk = blockIdx.x;
+  const long long S = (long long)d * h * wd, n = (long long)NB * S;
+  const long long i0 = n * chunk / chunks, i1 = n * (chunk + 1) / chunks;
+  float acc[27];
+#pragma unroll
+  for (int t = 0; t < 27; ++t) acc[t] = 0.f;
+  for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
+    const long long nb = i / S; long long v = i - nb * S;
     const int xx = (int)(v % wd); v /= wd;
     const int yy = (int)(v % h); const int zz = (int)(v / h);
-    const int z = zz + oz, yq = yy + oy, xq = xx + ox;
-    if (z >= 0 && z < d && yq >= 0 && yq < h && xq >= 0 && xq < wd) {
-      const long long base = (nb * CH + c) * S;
-      s = fmaf(x[base + ((long long)z * h + yq) * wd + xq], dy[base + ((long long)zz * h + yy) * wd + xx], s);
+    const long long base = (nb * CH + c) * S;
+    const float g = dy[base + ((long long)zz * h + yy) * wd + xx];
+#pragma unroll
+    for (int t = 0; t < 27; ++t) {
+      const int z = zz + t / 9 - 1, yq = yy + (t / 3) % 3 - 1, xq = xx + t % 3 - 1;
+      if (z >= 0 && z < d && yq >= 0 && yq < h && xq >= 0 && xq < wd) acc[t] = fmaf(x[base + ((long long)z * h + yq) * wd + xq], g, acc[t]);
     }
   }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) dw[blockIdx.x] = s;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int t = 0; t < 27; ++t) {
+    const float v = warp_sum(acc[t]);
+    if (lane == 0) red[wid][t] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    float v = 0.f;
+    for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+    part[((long long)c * chunks + chunk) * 27 + threadIdx.x] = v;
+  }
 }
-ICL_API int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int NB, int CH, int d, int h, int wd, void* stream) {
-  dwconv3d_wgrad_k<<<CH * 27, 256, 0, as_stream(stream)>>>(x, dy, dw, NB, CH, d, h, wd);
+// out[j] = sum_chunk part[(j / width) * chunks * width + chunk * width + j % width]   (one thread per output, fixed order)
+__global__ void reduce_chunks_k(const float* __restrict__ part, float* __restrict__ out, int groups, int width, int chunks) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= groups * width) return;
+  const int gidx = j / width, e = j % width;
+  const float* p = part + (long long)gidx * chunks * width + e;
+  float a = 0.f;
+  for (int cidx = 0; cidx < chunks; ++cidx) a += p[(long long)cidx * width];
+  out[j] = a;
+}
+ICL_API int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int NB, int CH, int d, int h, int wd, float* ws, void* stream) {
+  ICL_REQUIRE(ws != nullptr, "dwconv3d_wgrad: workspace of icl_reduce_workspace_bytes() bytes required");
+  const int chunks = red_chunks((long long)NB * d * h * wd, 2048);
+  ICL_REQUIRE((long long)CH * chunks * 27 * 4 <= RED_WS_BYTES, "dwconv3d_wgrad: CH=%d too large for the reduction workspace", CH);
+  dwconv3d_wgrad_partial_k<<<dim3(chunks, CH), 256, 0, as_stream(stream)>>>(x, dy, ws, NB, CH, d, h, wd, chunks);
+  icl_count_launch(1);
+  reduce_chunks_k<<<cdiv(CH * 27, 128), 128, 0, as_stream(stream)>>>(ws, dw, CH, 27, chunks);
   ICL_LAUNCHED("dwconv3d_wgrad");
 }
 
@@ -328,29 +376,62 @@ ICL_API int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int N
 // BatchNorm3d in training mode + ReLU on planar [NB, CH, S]: batch statistics per channel over
 // NB*S (biased var for normalisation, unbiased for the running update, momentum 0.1).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(512) bn_stats_k(const float* __restrict__ x, float* __restrict__ mean_rstd, float* __restrict__ run_mean,
-                                                  float* __restrict__ run_var, int NB, int CH, long long S, float eps, float momentum) {
+// partial sums of (a, b) over a chunk of positions of channel c: MODE 0: (x, x^2); MODE 1: (g, g * xhat) with g = dy * [y > 0]
+template <int MODE>
+__global__ void __launch_bounds__(256) bn_partial_k(const float* __restrict__ x, const float* __restrict__ dy, const float* __restrict__ y,
+                                                    const float* __restrict__ mean_rstd, double* __restrict__ part, int NB, int CH, long long S,
+                                                    int chunks) {
   __shared__ double red[66];
-  const int c = blockIdx.x;
+  const int c = blockIdx.y, chunk = blockIdx.x;
   const long long n = (long long)NB * S;
+  const long long i0 = n * chunk / chunks, i1 = n * (chunk + 1) / chunks;
+  float m = 0.f, r = 1.f;
+  if (MODE == 1) { m = mean_rstd[2 * c]; r = mean_rstd[2 * c + 1]; }
   double a = 0.0, q = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = x[((i / S) * CH + c) * S + (i % S)];
-    a += v; q += (double)v * v;
+  for (long long nb = i0 / S; nb * S < i1; ++nb) {
+    const long long lo = i0 > nb * S ? i0 : nb * S, hi = i1 < (nb + 1) * S ? i1 : (nb + 1) * S;
+    const long long base = (nb * CH + c) * S - nb * S;
+    float fa = 0.f, fq = 0.f;
+    for (long long i = lo + threadIdx.x; i < hi; i += 256) {
+      if (MODE == 0) {
+        const float v = x[base + i];
+        fa += v; fq = fmaf(v, v, fq);
+      } else {
+        const float g = y[base + i] > 0.f ? dy[base + i] : 0.f;
+        fa += g; fq = fmaf(g, (x[base + i] - m) * r, fq);
+      }
+    }
+    a += (double)fa; q += (double)fq;
   }
   a = block_sum_d(a, red); q = block_sum_d(q, red + 33);
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0) { part[((long long)c * chunks + chunk) * 2] = a; part[((long long)c * chunks + chunk) * 2 + 1] = q; }
+}
+// one warp per channel adds the chunk partials in a fixed order
+__global__ void bn_stats_finalize_k(const double* __restrict__ part, int chunks, float* __restrict__ mean_rstd, float* __restrict__ run_mean,
+                                    float* __restrict__ run_var, double n, float eps, float momentum) {
+  const int c = blockIdx.x, lane = threadIdx.x;
+  double a = 0.0, q = 0.0;
+  for (int i = lane; i < chunks; i += 32) { a += part[((long long)c * chunks + i) * 2]; q += part[((long long)c * chunks + i) * 2 + 1]; }
+  a = warp_sum_d(a); q = warp_sum_d(q);
+  if (lane == 0) {
     const double m = a / n;
     double var = q / n - m * m;
     if (var < 0) var = 0;
     mean_rstd[2 * c] = (float)m;
     mean_rstd[2 * c + 1] = (float)(1.0 / sqrt(var + (double)eps));
     if (run_mean) {
-      const double unb = n > 1 ? var * (double)n / (double)(n - 1) : var;
+      const double unb = n > 1 ? var * n / (n - 1) : var;
       run_mean[c] = (1.f - momentum) * run_mean[c] + momentum * (float)m;
       run_var[c] = (1.f - momentum) * run_var[c] + momentum * (float)unb;
     }
   }
+}
+__global__ void bn_bwd_finalize_k(const double* __restrict__ part, int chunks, float* __restrict__ sums) {
+  const int c = blockIdx.x, lane = threadIdx.x;
+  double a = 0.0, q = 0.0;
+  for (int i = lane; i < chunks; i += 32) { a += part[((long long)c * chunks + i) * 2]; q += part[((long long)c * chunks + i) * 2 + 1]; }
+  a = warp_sum_d(a); q = warp_sum_d(q);
+  if (lane == 0) { sums[2 * c] = (float)a; sums[2 * c + 1] = (float)q; }
 }
 __global__ void bn_relu_apply_k(const float* __restrict__ x, const float* __restrict__ mean_rstd, const float* __restrict__ g,
                                 const float* __restrict__ b, float* __restrict__ y, int CH, long long S, long long total) {
@@ -360,29 +441,19 @@ __global__ void bn_relu_apply_k(const float* __restrict__ x, const float* __rest
   }
 }
 ICL_API int icl_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd, float* run_mean, float* run_var,
-                            int NB, int CH, long long S, float eps, float momentum, void* stream) {
-  bn_stats_k<<<CH, 512, 0, as_stream(stream)>>>(x, mean_rstd, run_mean, run_var, NB, CH, S, eps, momentum);
+                            int NB, int CH, long long S, float eps, float momentum, double* ws, void* stream) {
+  ICL_REQUIRE(ws != nullptr, "bn_relu_fwd: workspace of icl_reduce_workspace_bytes() bytes required");
+  const int chunks = red_chunks((long long)NB * S, 4096);
+  ICL_REQUIRE((long long)CH * chunks * 16 <= RED_WS_BYTES, "bn_relu_fwd: CH=%d too large for the reduction workspace", CH);
+  bn_partial_k<0><<<dim3(chunks, CH), 256, 0, as_stream(stream)>>>(x, nullptr, nullptr, nullptr, ws, NB, CH, S, chunks);
+  icl_count_launch(1);
+  bn_stats_finalize_k<<<CH, 32, 0, as_stream(stream)>>>(ws, chunks, mean_rstd, run_mean, run_var, (double)NB * (double)S, eps, momentum);
   icl_count_launch(1);
   const long long total = (long long)NB * CH * S;
   bn_relu_apply_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(x, mean_rstd, gamma, beta, y, CH, S, total);
   ICL_LAUNCHED("bn_relu_fwd");
 }
 // backward: g = dy * [y > 0];  dgamma = sum g*xh; dbeta = sum g; dx = gamma*rstd*(g - mean(g) - xh*mean(g*xh))
-__global__ void __launch_bounds__(512) bn_relu_bwd_reduce_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
-                                                            const float* __restrict__ mean_rstd, float* __restrict__ sums, int NB, int CH, long long S) {
-  __shared__ double red[66];
-  const int c = blockIdx.x;
-  const long long n = (long long)NB * S;
-  const float m = mean_rstd[2 * c], r = mean_rstd[2 * c + 1];
-  double a = 0.0, q = 0.0;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
-    const long long o = ((i / S) * CH + c) * S + (i % S);
-    const float g = y[o] > 0.f ? dy[o] : 0.f;
-    a += g; q += (double)g * ((x[o] - m) * r);
-  }
-  a = block_sum_d(a, red); q = block_sum_d(q, red + 33);
-  if (threadIdx.x == 0) { sums[2 * c] = (float)a; sums[2 * c + 1] = (float)q; }
-}
 __global__ void bn_relu_bwd_apply_k(const float* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ y,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ g, const float* __restrict__ sums,
                                     float* __restrict__ dx, int CH, long long S, long long total, float inv_n) {
@@ -395,8 +466,13 @@ __global__ void bn_relu_bwd_apply_k(const float* __restrict__ dy, const float* _
   }
 }
 ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums /*[CH,2]: dbeta,dgamma*/,
-                            float* dx, int NB, int CH, long long S, void* stream) {
-  bn_relu_bwd_reduce_k<<<CH, 512, 0, as_stream(stream)>>>(dy, x, y, mean_rstd, sums, NB, CH, S);
+                            float* dx, int NB, int CH, long long S, double* ws, void* stream) {
+  ICL_REQUIRE(ws != nullptr, "bn_relu_bwd: workspace of icl_reduce_workspace_bytes() bytes required");
+  const int chunks = red_chunks((long long)NB * S, 4096);
+  ICL_REQUIRE((long long)CH * chunks * 16 <= RED_WS_BYTES, "bn_relu_bwd: CH=%d too large for the reduction workspace", CH);
+  bn_partial_k<1><<<dim3(chunks, CH), 256, 0, as_stream(stream)>>>(x, dy, y, mean_rstd, ws, NB, CH, S, chunks);
+  icl_count_launch(1);
+  bn_bwd_finalize_k<<<CH, 32, 0, as_stream(stream)>>>(ws, chunks, sums);
   icl_count_launch(1);
   const long long total = (long long)NB * CH * S;
   bn_relu_bwd_apply_k<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(dy, x, y, mean_rstd, gamma, sums, dx, CH, S, total,
@@ -404,24 +480,62 @@ ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, con
   ICL_LAUNCHED("bn_relu_bwd");
 }
 
-// pointwise (1x1x1) weight gradient on planar maps: dw[o][i] = sum_{nb, s} dy[nb,o,s] * x[nb,i,s]; db[o] = sum dy
-__global__ void __launch_bounds__(256) planar_pw_wgrad_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dw,
-                                                         float* __restrict__ db, int NB, int CO, int CI, long long S) {
-  __shared__ float red[33];
-  const int o = blockIdx.x / (CI + 1), i = blockIdx.x % (CI + 1);
-  float s = 0.f;
-  for (long long k = threadIdx.x; k < (long long)NB * S; k += blockDim.x) {
-    const long long nb = k / S, sp = k % S;
-    const float g = dy[(nb * CO + o) * S + sp];
-    s += (i < CI) ? g * x[(nb * CI + i) * S + sp] : g;
+// pointwise (1x1x1) weight gradient on planar maps: dw[o][i] = sum_{nb, s} dy[nb,o,s] * x[nb,i,s]; db[o] = sum dy.
+// Block = chunk of positions; the dy / x values of 256 positions are staged in shared memory, then thread (o, i) adds its products
+// (CO * (CI + 1) <= 272 pairs, threads stride over them) -> partial[chunk][CO * (CI + 1)]; reduce_chunks_k finishes.
+#define PW_T 256
+__global__ void __launch_bounds__(256) planar_pw_wgrad_partial_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part,
+                                                                 int NB, int CO, int CI, long long S, int chunks) {
+  extern __shared__ float sm[];  // [CO][PW_T] dy, then [CI][PW_T] x
+  float* sdy = sm;
+  float* sx = sm + CO * PW_T;
+  const int chunk = blockIdx.x;
+  const long long n = (long long)NB * S;
+  const long long i0 = n * chunk / chunks, i1 = n * (chunk + 1) / chunks;
+  const int pairs = CO * (CI + 1);
+  float acc0 = 0.f, acc1 = 0.f;   // pairs threadIdx.x and threadIdx.x + 256
+  for (long long t0 = i0; t0 < i1; t0 += PW_T) {
+    const long long p = t0 + threadIdx.x;
+    const bool ok = p < i1;
+    const long long nb = ok ? p / S : 0, sp = ok ? p - nb * S : 0;
+    for (int o = 0; o < CO; ++o) sdy[o * PW_T + threadIdx.x] = ok ? dy[(nb * CO + o) * S + sp] : 0.f;
+    for (int i = 0; i < CI; ++i) sx[i * PW_T + threadIdx.x] = ok ? x[(nb * CI + i) * S + sp] : 0.f;
+    __syncthreads();
+    for (int pr = threadIdx.x, k = 0; pr < pairs; pr += 256, ++k) {
+      const int o = pr / (CI + 1), i = pr % (CI + 1);
+      const float* a = sdy + o * PW_T;
+      float s = 0.f;
+      if (i < CI) {
+        const float* b = sx + i * PW_T;
+#pragma unroll 8
+        for (int t = 0; t < PW_T; ++t) s = fmaf(a[t], b[t], s);
+      } else {
+#pragma unroll 8
+        for (int t = 0; t < PW_T; ++t) s += a[t];
+      }
+      if (k == 0) acc0 += s; else acc1 += s;
+    }
+    __syncthreads();
   }
-  s = block_sum(s, red);
-  if (threadIdx.x == 0) {
-    if (i < CI) dw[o * CI + i] = s;
-    else if (db) db[o] = s;
-  }
+  if (threadIdx.x < pairs) part[(long long)chunk * pairs + threadIdx.x] = acc0;
+  if (threadIdx.x + 256 < pairs) part[(long long)chunk * pairs + threadIdx.x + 256] = acc1;
 }
-ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, void* stream) {
-  planar_pw_wgrad_k<<<CO * (CI + 1), 256, 0, as_stream(stream)>>>(dy, x, dw, db, NB, CO, CI, S);
+__global__ void planar_pw_finalize_k(const float* __restrict__ part, int chunks, int CO, int CI, float* __restrict__ dw, float* __restrict__ db) {
+  const int pr = blockIdx.x * blockDim.x + threadIdx.x, pairs = CO * (CI + 1);
+  if (pr >= pairs) return;
+  float a = 0.f;
+  for (int c = 0; c < chunks; ++c) a += part[(long long)c * pairs + pr];
+  const int o = pr / (CI + 1), i = pr % (CI + 1);
+  if (i < CI) dw[o * CI + i] = a;
+  else if (db) db[o] = a;
+}
+ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, float* ws, void* stream) {
+  ICL_REQUIRE(ws != nullptr, "planar_pw_wgrad: workspace of icl_reduce_workspace_bytes() bytes required");
+  ICL_REQUIRE(CO >= 1 && CI >= 1 && CO * (CI + 1) <= 512 && (CO + CI) * PW_T * 4 <= 48 * 1024, "planar_pw_wgrad: CO=%d CI=%d not supported", CO, CI);
+  const int chunks = red_chunks((long long)NB * S, 4 * PW_T);
+  ICL_REQUIRE((long long)chunks * CO * (CI + 1) * 4 <= RED_WS_BYTES, "planar_pw_wgrad: workspace too small");
+  planar_pw_wgrad_partial_k<<<chunks, 256, (size_t)(CO + CI) * PW_T * 4, as_stream(stream)>>>(dy, x, ws, NB, CO, CI, S, chunks);
+  icl_count_launch(1);
+  planar_pw_finalize_k<<<cdiv(CO * (CI + 1), 128), 128, 0, as_stream(stream)>>>(ws, chunks, CO, CI, dw, db);
   ICL_LAUNCHED("planar_pw_wgrad");
 }

@@ -242,7 +242,8 @@ class DwConv3dFn(torch.autograd.Function):
             dx = torch.empty_like(x_)
             call("icl_dwconv3d", P(dy), P(w_), P(dx), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd), c_int(1))
         dw = torch.empty_like(w_)
-        call("icl_dwconv3d_wgrad", P(x_), P(dy), P(dw), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd))
+        call("icl_dwconv3d_wgrad", P(x_), P(dy), P(dw), c_int(NB), c_int(CH), c_int(d), c_int(h), c_int(wd), P(ops.reduce_ws(x_.device)),
+             mbytes=8e-6 * x_.numel(), tag="NB%d CH%d r%d" % (NB, CH, d))
         return dx, dw
 
 
@@ -263,7 +264,7 @@ class BnReluFn(torch.autograd.Function):
         mr = torch.empty((CH, 2), dtype=torch.float32, device=x.device)
         if training:
             call("icl_bn_relu_fwd", P(x_), P(gamma.detach()), P(beta.detach()), P(y), P(mr), P(run_mean), P(run_var), c_int(NB), c_int(CH),
-                 c_ll(S), c_f(eps), c_f(momentum))
+                 c_ll(S), c_f(eps), c_f(momentum), P(ops.reduce_ws(x_.device)), mbytes=12e-6 * x_.numel(), tag="NB%d CH%d S%d" % (NB, CH, S))
         else:
             raise RuntimeError("icl_b200 BatchNorm: eval-mode ICL heads are not on the reference's path "
                                "(inference returns before the heads, unet_3D_icl.py:119-120)")
@@ -277,7 +278,9 @@ class BnReluFn(torch.autograd.Function):
         NB, CH, S = ctx.dims
         sums = torch.empty((CH, 2), dtype=torch.float32, device=x_.device)
         dx = torch.empty_like(x_)
-        call("icl_bn_relu_bwd", P(_c(dy)), P(x_), P(y), P(mr), P(gamma), P(sums), P(dx), c_int(NB), c_int(CH), c_ll(S))
+        dy_c = _c(dy)
+        call("icl_bn_relu_bwd", P(dy_c), P(x_), P(y), P(mr), P(gamma), P(sums), P(dx), c_int(NB), c_int(CH), c_ll(S), P(ops.reduce_ws(x_.device)),
+             mbytes=28e-6 * x_.numel(), tag="NB%d CH%d S%d" % (NB, CH, S))
         return dx, sums[:, 1].contiguous(), sums[:, 0].contiguous(), None, None, None, None, None
 
 
@@ -317,7 +320,8 @@ class PlanarPointwiseFn(torch.autograd.Function):
             ops.sgemm(CI, S, CO, w2, 1, CI, dy, S, 1, dx, S, 1, batch=NB, sA=0, sB=CO * S, sC=CI * S)
         dw = torch.empty_like(w2)
         db = torch.empty((CO,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
-        call("icl_planar_pw_wgrad", P(dy), P(x_), P(dw), P(db), c_int(NB), c_int(CO), c_int(CI), c_ll(S))
+        call("icl_planar_pw_wgrad", P(dy), P(x_), P(dw), P(db), c_int(NB), c_int(CO), c_int(CI), c_ll(S), P(ops.reduce_ws(x_.device)),
+             mbytes=4e-6 * NB * S * (CO + CI), tag="NB%d %d->%d S%d" % (NB, CI, CO, S))
         return dx, dw.reshape(ctx.wshape), db
 
 

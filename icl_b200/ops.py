@@ -24,6 +24,12 @@ def _require_cuda(t):
         raise RuntimeError("icl_b200 ops run on CUDA tensors only (no CPU fallback); got a %s tensor" % t.device)
 
 
+def reduce_ws(device):
+    """Scratch for the chunked two-stage reductions of the ICL-head kernels (heads.cu); allocated per call from torch's caching
+    allocator (stream-ordered, CUDA-graph safe)."""
+    return torch.empty((_lib.lib().icl_reduce_workspace_bytes(),), dtype=torch.uint8, device=device)
+
+
 def to_ndhwc(x):
     """[B,C,D,H,W] (any strides) -> contiguous [B,D,H,W,C] float32 (no copy if already channels-last)."""
     _require_cuda(x)

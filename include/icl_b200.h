@@ -135,12 +135,14 @@ int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* map, co
 
 /* ---- SeparableConv3d (depthwise 3^3 + BatchNorm3d(train) + ReLU + pointwise + BN + ReLU): networks/unet_3D_icl.py:317-345 ---- */
 int icl_dwconv3d(const float* x, const float* w, float* y, int NB, int CH, int d, int h, int wd, int flip, void* stream);
-int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int NB, int CH, int d, int h, int wd, void* stream);
+/* `ws`: device scratch of icl_reduce_workspace_bytes() bytes (chunked two-stage reductions over all (sample, voxel) positions) */
+int icl_reduce_workspace_bytes(void);
+int icl_dwconv3d_wgrad(const float* x, const float* dy, float* dw, int NB, int CH, int d, int h, int wd, float* ws, void* stream);
 int icl_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float* y, float* mean_rstd, float* run_mean, float* run_var, int NB,
-                    int CH, long long S, float eps, float momentum, void* stream);
+                    int CH, long long S, float eps, float momentum, double* ws, void* stream);
 int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums, float* dx, int NB,
-                    int CH, long long S, void* stream);
-int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, void* stream);
+                    int CH, long long S, double* ws, void* stream);
+int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, float* ws, void* stream);
 
 /* ---- losses: CrossEntropyLoss + DiceLoss (utils/losses.py:195-231), AuxLoss3D (:254-271, trilinear
         interpolation fused), PseudoSoftLoss3D / softmax_dice_loss (:287-299, :42-59), softmax_mse_loss (:68-90) ---- */

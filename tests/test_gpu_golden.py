@@ -158,7 +158,10 @@ def test_full_step_golden(name):
                 bad.append("%s: zero-gradient bias has l2 %.3e (ref %.3e)" % (k, p.grad.norm().item(), float(g["gsum/" + k][1])))
             continue
         try:
-            check_summary(p.grad, g["gsum/" + k], g["gval/" + k], 5e-3, k, abs_floor=5e-6)
+            # sanity bound only (ReLU-derivative / MaxPool-winner flips between two correct implementations move individual gradient
+            # entries by their full size; K = 16 with random labels has the noisier loss gradient): the backward
+            # ARITHMETIC is pinned at 1e-3 by test_backbone_grads_mask_matched, where those discrete choices are held fixed
+            check_summary(p.grad, g["gsum/" + k], g["gval/" + k], 5e-3 if K == 2 else 1e-2, k, abs_floor=5e-6)
         except AssertionError as e:
             bad.append(str(e))
     assert not bad, "\n".join(bad[:20])
