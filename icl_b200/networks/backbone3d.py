@@ -70,7 +70,7 @@ def _half_bwd(h, dA, need_dx):
     cout = h.w.shape[0]
     B, D, H, W, _ = h.y.shape
     dgrad_umma = need_dx and ops.umma_ok([cout], sum(cins), with_stats=False) and all(c % 16 == 0 for c in cins)
-    wgrad_umma = ops.wgrad_umma_ok(cins, cout) and all(s.pk is not None for s in h.srcs)
+    wgrad_umma = ops.wgrad_umma_ok(cins, cout, D) and all(s.pk is not None for s in h.srcs)
     if wgrad_umma:
         # fp32 dY is only read by the CUDA-core data-gradient fallback
         dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True, want_f32=need_dx and not dgrad_umma)
@@ -134,7 +134,9 @@ class Backbone3DFn(torch.autograd.Function):
         B, D, H, W, Cin = x_.shape
         # every conv from the second one on runs on the tensor cores when all channel counts are multiples of 16:
         # pooled / upsampled tensors are then only ever read as PK operands and their fp32 copies are not written
-        lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16)
+        # (the tensor-core weight gradient needs an even depth at every level: with D % 32 != 0 the `center` level has an odd
+        # depth, its weight gradient runs on the CUDA-core kernel and reads the fp32 copies, so they must exist)
+        lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16, D // 16)
         if D % 16 or H % 16 or W % 16:
             raise RuntimeError("unet_3D backbone: spatial size must be a multiple of 16, got %s" % ((D, H, W),))
         rec = {}

@@ -156,10 +156,11 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     return dw, db
 
 
-def wgrad_umma_ok(cins, cout):
+def wgrad_umma_ok(cins, cout, D=2):
+    """Shapes the tcgen05 weight-gradient kernel takes: channel multiples of 16 and an EVEN depth (it walks two planes per step)."""
     if os.environ.get("ICL_DISABLE_UMMA") == "1" or not tensor_cores():
         return False
-    return all(c % 16 == 0 for c in cins) and cout % 16 == 0
+    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and D % 2 == 0
 
 
 def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W):
