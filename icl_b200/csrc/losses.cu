@@ -8,6 +8,7 @@
 // per-class partial sums reduced warp -> block -> one double atomic per block.
 // Reference: utils/losses.py:22-30,42-59,68-90,195-231,254-299.
 #include "common.cuh"
+#include <stdlib.h>
 
 struct SrcGeom {
   int planar;          // 1: [B,K,rz,ry,rx]   0: channels-last [B,rz,ry,rx,K]
@@ -322,6 +323,246 @@ __global__ void __launch_bounds__(256) class_stats_bwd_k(const float* __restrict
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Row form of the class-statistics kernels (the path every BASELINE shape takes: X <= 256).
+// A block walks over whole x-rows (b, z, y) of the loss grid, threads along x.  For an interpolated source the z / y
+// interpolation of the row is done ONCE per row into a shared-memory table tab[k][cx] (K * rx values from the four coarse
+// rows), so a voxel costs 2 shared-memory reads per class instead of 8 global ones; labels / soft targets / direct logits
+// are read with full-width vector loads (a voxel's K contiguous channels-last values = one or more float4).
+// Backward: the per-voxel gradient of the row goes to shared memory and the x-axis adjoint of the interpolation
+// (X -> rx) is applied inside the block; the kernel writes [B][K][Z][Y][rx] (X / rx times smaller than the fine gradient
+// the old two-stage path wrote), and trilinear_adjoint_k finishes the y / z adjoint on that reduced tensor.
+// ------------------------------------------------------------------------------------------
+#define ROW_MAXX 256
+#define ROW_TABW 129   // rx <= X / 2 <= 128 (+1: odd stride, conflict-free columns)
+
+template <int KT>
+__device__ __forceinline__ void load_vec(const float* __restrict__ p, int K, float* L) {
+  if (K == KT && KT % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < KT; k += 4) {
+      const float4 v = *reinterpret_cast<const float4*>(p + k);
+      L[k] = v.x; L[k + 1] = v.y; L[k + 2] = v.z; L[k + 3] = v.w;
+    }
+  } else if (K == KT && KT == 2) {
+    const float2 v = *reinterpret_cast<const float2*>(p);
+    L[0] = v.x; L[1] = v.y;
+  } else {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) L[k] = p[k];
+  }
+}
+template <int KT>
+__device__ __forceinline__ void store_vec(float* __restrict__ p, int K, const float* L) {
+  if (K == KT && KT % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < KT; k += 4) *reinterpret_cast<float4*>(p + k) = make_float4(L[k], L[k + 1], L[k + 2], L[k + 3]);
+  } else if (K == KT && KT == 2) {
+    *reinterpret_cast<float2*>(p) = make_float2(L[0], L[1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) p[k] = L[k];
+  }
+}
+
+// tab[k][cx] = z/y-interpolated coarse row for fine row (z, y) of sample b.  All threads of the block; caller syncs.
+template <int KT>
+__device__ __forceinline__ void row_table(const float* __restrict__ src, const SrcGeom& g, int K, int b, int z, int y, float* tab) {
+  int z0, z1, y0, y1; float lz, ly;
+  lin_src(z, g.sz, g.rz, z0, z1, lz); lin_src(y, g.sy, g.ry, y0, y1, ly);
+  const float w00 = (1.f - lz) * (1.f - ly), w01 = (1.f - lz) * ly, w10 = lz * (1.f - ly), w11 = lz * ly;
+  const long long Sr = (long long)g.rz * g.ry * g.rx;
+  const long long r00 = ((long long)z0 * g.ry + y0) * g.rx, r01 = ((long long)z0 * g.ry + y1) * g.rx;
+  const long long r10 = ((long long)z1 * g.ry + y0) * g.rx, r11 = ((long long)z1 * g.ry + y1) * g.rx;
+  const int n = K * g.rx;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int k, cx; long long st; const float* p;
+    if (g.planar) { k = i / g.rx; cx = i - k * g.rx; p = src + ((long long)b * K + k) * Sr + cx; st = 1; }
+    else { cx = i / K; k = i - cx * K; p = src + (long long)b * Sr * K + (long long)cx * K + k; st = K; }
+    tab[k * ROW_TABW + cx] = w00 * p[r00 * st] + w01 * p[r01 * st] + w10 * p[r10 * st] + w11 * p[r11 * st];
+  }
+}
+
+template <int KT>
+__device__ __forceinline__ void row_logits(const float* __restrict__ src, const SrcGeom& g, bool direct, int K, long long vox_in_batch, int b,
+                                           int x, const float* tab, float* L) {
+  if (direct) {
+    const long long S = (long long)g.Z * g.Y * g.X;
+    if (g.planar) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) if (k < K) L[k] = src[((long long)b * K + k) * S + vox_in_batch];
+    } else {
+      load_vec<KT>(src + ((long long)b * S + vox_in_batch) * K, K, L);
+    }
+  } else {
+    int x0, x1; float lx;
+    lin_src(x, g.sx, g.rx, x0, x1, lx);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) L[k] = (1.f - lx) * tab[k * ROW_TABW + x0] + lx * tab[k * ROW_TABW + x1];
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(256, 2) class_stats_row_fwd_k(const float* __restrict__ src, SrcGeom g, int B, int K,
+                                                             const long long* __restrict__ labels, const float* __restrict__ tgt,
+                                                             int is_prob, double* __restrict__ sums) {
+  __shared__ float tab[KT * ROW_TABW];
+  __shared__ float red[8][3 * KT + 1];
+  float acc[3 * KT + 1];
+#pragma unroll
+  for (int i = 0; i < 3 * KT + 1; ++i) acc[i] = 0.f;
+  const bool direct = g.rz == g.Z && g.ry == g.Y && g.rx == g.X;
+  const long long rows = (long long)B * g.Z * g.Y;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / ((long long)g.Z * g.Y));
+    const int zy = (int)(row - (long long)b * g.Z * g.Y);
+    const int z = zy / g.Y, y = zy - z * g.Y;
+    if (!direct) {
+      __syncthreads();   // the previous row's readers are done with the table
+      row_table<KT>(src, g, K, b, z, y, tab);
+      __syncthreads();
+    }
+    for (int x = threadIdx.x; x < g.X; x += blockDim.x) {
+      const long long v = (long long)zy * g.X + x, i = row * g.X + x;
+      float L[KT];
+      row_logits<KT>(src, g, direct, K, v, b, x, tab, L);
+      float mx, lse;
+      if (labels) {
+        const int lab = (int)labels[i];
+        float raw = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) if (k == lab) raw = L[k];
+        if (!is_prob) {
+          softmax_inplace<KT>(L, K, mx, lse);
+          acc[0] += (mx + lse) - raw;
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) if (k < K) {
+          const float t = (k == lab) ? 1.f : 0.f;
+          acc[1 + 3 * k] += L[k] * t; acc[2 + 3 * k] += L[k] * L[k]; acc[3 + 3 * k] += t;
+        }
+      } else {
+        float Q[KT];
+        load_vec<KT>(tgt + i * K, K, Q);
+        softmax_inplace<KT>(L, K, mx, lse);
+        softmax_inplace<KT>(Q, K, mx, lse);
+#pragma unroll
+        for (int k = 0; k < KT; ++k) if (k < K) { acc[1 + 3 * k] += L[k] * Q[k]; acc[2 + 3 * k] += L[k]; acc[3 + 3 * k] += Q[k]; }
+      }
+    }
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 3 * KT + 1; ++i) {
+    const float sv = warp_sum(acc[i]);
+    if (lane == 0) red[wid][i] = sv;
+  }
+  __syncthreads();
+  if (threadIdx.x < 3 * K + 1) {
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += (double)red[w][threadIdx.x];
+    atomicAdd(&sums[threadIdx.x], t);
+  }
+}
+
+// gradient w.r.t. the logits of one voxel from its (already loaded) logits L (overwritten with probabilities)
+template <int KT>
+__device__ __forceinline__ void dlogits_from(float* L, int K, long long i, const long long* __restrict__ labels, const float* __restrict__ tgt,
+                                             int is_prob, const float* cA, const float* cB, float cCE, float* dl) {
+  float mx, lse;
+  if (!is_prob) softmax_inplace<KT>(L, K, mx, lse);
+  float dot = 0.f;
+  if (labels) {
+    const int lab = (int)labels[i];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) {
+      dl[k] = cA[k] * ((k == lab) ? 1.f : 0.f) + cB[k] * 2.f * L[k];
+      dot += dl[k] * L[k];
+    }
+    if (!is_prob) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k) if (k < K) dl[k] = L[k] * (dl[k] - dot) + cCE * (L[k] - ((k == lab) ? 1.f : 0.f));
+    }
+  } else {
+    float Q[KT];
+    load_vec<KT>(tgt + i * K, K, Q);
+    softmax_inplace<KT>(Q, K, mx, lse);
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) { dl[k] = cA[k] * Q[k] + cB[k]; dot += dl[k] * L[k]; }
+#pragma unroll
+    for (int k = 0; k < KT; ++k) if (k < K) dl[k] = L[k] * (dl[k] - dot);
+  }
+}
+
+// direct sources: dsrc (layout of src) = per-voxel gradient.  Interpolated sources: xred[b][k][z][y][cx] = x-adjoint of the row.
+template <int KT>
+__global__ void __launch_bounds__(256, 2) class_stats_row_bwd_k(const float* __restrict__ src, SrcGeom g, int B, int K,
+                                                             const long long* __restrict__ labels, const float* __restrict__ tgt,
+                                                             int is_prob, const float* __restrict__ class_w, const double* __restrict__ sums,
+                                                             const float* __restrict__ g_ce, const float* __restrict__ g_dice, float w_ce,
+                                                             float w_dice, float* __restrict__ dsrc, float* __restrict__ xred) {
+  __shared__ float cA[KT], cB[KT];
+  __shared__ float cCE;
+  __shared__ float tab[KT * ROW_TABW];
+  extern __shared__ float sdl[];   // [KT][X + 1] per-voxel gradients of the current row (interpolated sources only)
+  const bool direct = g.rz == g.Z && g.ry == g.Y && g.rx == g.X;
+  if (threadIdx.x < K) {
+    const int k = threadIdx.x;
+    const double num = 2.0 * sums[1 + 3 * k] + 1e-5, den = sums[2 + 3 * k] + sums[3 + 3 * k] + 1e-5;
+    const double gd = (g_dice ? (double)g_dice[0] : 0.0) * w_dice / K * (class_w ? (double)class_w[k] : 1.0);
+    cA[k] = (float)(-2.0 * gd / den);
+    cB[k] = (float)(gd * num / (den * den));
+  }
+  if (threadIdx.x == 0) cCE = (g_ce && labels && !is_prob) ? g_ce[0] * w_ce / (float)((double)B * g.Z * g.Y * g.X) : 0.f;
+  __syncthreads();
+  const long long rows = (long long)B * g.Z * g.Y, S = (long long)g.Z * g.Y * g.X;
+  const int XS = g.X + 1, fx = direct ? 1 : g.X / g.rx;
+  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+    const int b = (int)(row / ((long long)g.Z * g.Y));
+    const int zy = (int)(row - (long long)b * g.Z * g.Y);
+    const int z = zy / g.Y, y = zy - z * g.Y;
+    if (!direct) {
+      __syncthreads();   // previous row: table readers and sdl readers are done
+      row_table<KT>(src, g, K, b, z, y, tab);
+      __syncthreads();
+    }
+    for (int x = threadIdx.x; x < g.X; x += blockDim.x) {
+      const long long v = (long long)zy * g.X + x, i = row * g.X + x;
+      float L[KT], dl[KT];
+      row_logits<KT>(src, g, direct, K, v, b, x, tab, L);
+      dlogits_from<KT>(L, K, i, labels, tgt, is_prob, cA, cB, cCE, dl);
+      if (direct) {
+        if (g.planar) {
+#pragma unroll
+          for (int k = 0; k < KT; ++k) if (k < K) dsrc[((long long)b * K + k) * S + v] = dl[k];
+        } else {
+          store_vec<KT>(dsrc + ((long long)b * S + v) * K, K, dl);
+        }
+      } else {
+#pragma unroll
+        for (int k = 0; k < KT; ++k) if (k < K) sdl[k * XS + x] = dl[k];
+      }
+    }
+    if (!direct) {
+      __syncthreads();
+      // x-adjoint: coarse column cx collects the fine columns whose interpolation footprint touches it
+      const int n = K * g.rx;
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int k = i / g.rx, cx = i - k * g.rx;
+        const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
+        float a = 0.f;
+        for (int x = x0; x <= x1; ++x) {
+          int i0, i1; float l1;
+          lin_src(x, g.sx, g.rx, i0, i1, l1);
+          const float w = (i0 == cx ? 1.f - l1 : 0.f) + (i1 == cx ? l1 : 0.f);
+          a = fmaf(w, sdl[k * XS + x], a);
+        }
+        xred[(((long long)b * K + k) * g.Z * g.Y + zy) * g.rx + cx] = a;
+      }
+    }
+  }
+}
+
 static int make_geom(SrcGeom& g, int planar, int rz, int ry, int rx, int Z, int Y, int X) {
   g.planar = planar; g.rz = rz; g.ry = ry; g.rx = rx; g.Z = Z; g.Y = Y; g.X = X;
   g.sz = (float)rz / (float)Z; g.sy = (float)ry / (float)Y; g.sx = (float)rx / (float)X;
@@ -332,6 +573,14 @@ static int make_geom(SrcGeom& g, int planar, int rz, int ry, int rx, int Z, int 
     return -1;
   }
   return 0;
+}
+
+// the row kernels take every loss grid whose rows fit their shared-memory staging (all BASELINE shapes: X = 96 or 256)
+// (ICL_DISABLE_ROW_LOSS=1 routes everything to the generic per-voxel kernels — a test knob that keeps them covered)
+static inline bool row_path_ok(bool direct, int rx, int X) {
+  const char* e = getenv("ICL_DISABLE_ROW_LOSS");
+  if (e && e[0] == '1') return false;
+  return X <= ROW_MAXX && (direct || (rx <= ROW_TABW - 1 && 2 * rx <= X));
 }
 
 #define DISPATCH_K(K, CALL)                                      \
@@ -345,9 +594,19 @@ ICL_API int icl_class_stats_fwd(const float* src, int planar, int rz, int ry, in
   SrcGeom g;
   if (make_geom(g, planar, rz, ry, rx, Z, Y, X)) return -1;
   const long long total = (long long)B * Z * Y * X;
-#define CALL(KT) class_stats_fwd_k<KT><<<grid_for(total, 256, 148 * 8), 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, sums)
-  DISPATCH_K(K, CALL)
+  const bool direct = rz == Z && ry == Y && rx == X;
+  if (row_path_ok(direct, rx, X)) {
+    const int threads = X >= 256 ? 256 : ((X + 31) / 32) * 32;
+    const long long rows = (long long)B * Z * Y;
+    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+#define CALL(KT) class_stats_row_fwd_k<KT><<<grid, threads, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, sums)
+    DISPATCH_K(K, CALL)
 #undef CALL
+  } else {
+#define CALL(KT) class_stats_fwd_k<KT><<<grid_for(total, 256, 148 * 8), 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, sums)
+    DISPATCH_K(K, CALL)
+#undef CALL
+  }
   icl_count_launch(1);
   class_stats_finalize_k<<<1, 32, 0, as_stream(stream)>>>(sums, K, (double)total, class_w, out2);
   ICL_LAUNCHED("class_stats_fwd");
@@ -362,6 +621,29 @@ ICL_API int icl_class_stats_bwd(const float* src, int planar, int rz, int ry, in
   if (make_geom(g, planar, rz, ry, rx, Z, Y, X)) return -1;
   const long long blocks = (long long)B * cdiv(Z, BT_Z) * cdiv(Y, BT_Y) * cdiv(X, BT_X);
   const bool direct = rz == Z && ry == Y && rx == X;
+  if (row_path_ok(direct, rx, X) && (direct || (workspace && Z % rz == 0 && Y % ry == 0 && X % rx == 0))) {
+    const int threads = X >= 256 ? 256 : ((X + 31) / 32) * 32;
+    const long long rows = (long long)B * Z * Y;
+    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
+    const size_t smem = direct ? 0 : (size_t)16 * (X + 1) * sizeof(float);
+#define CALL(KT) class_stats_row_bwd_k<KT><<<grid, threads, direct ? 0 : (size_t)KT * (X + 1) * sizeof(float), as_stream(stream)>>>( \
+      src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, workspace)
+    DISPATCH_K(K, CALL)
+#undef CALL
+    (void)smem;
+    if (!direct) {
+      icl_count_launch(1);
+      // y / z adjoint on the x-reduced gradient [B][K][Z][Y][rx]: the same gather kernel with an untouched x axis
+      SrcGeom g2;
+      if (make_geom(g2, planar, rz, ry, rx, Z, Y, rx)) return -1;
+      const long long foot = 4LL * (Z / rz) * (Y / ry) * 3;
+      const int G = foot >= 4096 ? 256 : 32;
+      const long long cells = (long long)B * K * rz * ry * rx;
+      const long long nb = (cells + (256 / G) - 1) / (256 / G);
+      trilinear_adjoint_k<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(workspace, g2, K, dsrc, G, cells);
+    }
+    ICL_LAUNCHED("class_stats_bwd");
+  }
   float* fine = (!direct && workspace && Z % rz == 0 && Y % ry == 0 && X % rx == 0) ? workspace : nullptr;
 #define CALL(KT) class_stats_bwd_k<KT><<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, fine)
   DISPATCH_K(K, CALL)

@@ -152,7 +152,7 @@ def test_unet3d_icl_inference_flag(K):
     plain.load_state_dict({k: v for k, v in net.state_dict().items() if not (k.startswith("sspa") or k.startswith("uscl"))})
     plain.cuda().eval()
     with torch.no_grad():
-        assert_close(plain(x.cuda()).cpu(), out.cpu(), 1e-6, "unet_3D with the ICL checkpoint's backbone keys")
+        assert_close(plain(x.cuda()).cpu(), out.cpu(), 1e-4, "unet_3D with the ICL checkpoint's backbone keys")   # statistics use atomics
 
 
 def test_unet2d_eval_mode_running_stats():

@@ -485,10 +485,13 @@ def test_add_scaled_and_batch_mean():
 
 
 # ------------------------------------------------------------------------------------------ losses / optimiser / inference kernels
-@pytest.mark.parametrize("K", [2, 5, 16])
-def test_losses_small(K):
+@pytest.mark.parametrize("K,generic", [(2, False), (5, False), (16, False), (4, True), (16, True)])
+def test_losses_small(monkeypatch, K, generic):
+    """generic=True routes the class-statistics losses to the per-voxel kernels (grids whose rows exceed the row kernels' staging);
+    the default is the row form (z/y interpolation table in shared memory, x-adjoint inside the block)."""
     from icl_b200.utils import losses as L
     from oracle import restate as R
+    monkeypatch.setenv("ICL_DISABLE_ROW_LOSS", "1" if generic else "0")
     B, S = 2, 16
     size = (S, S, S)
     labels = torch.randint(0, K, (B, S, S, S), generator=g(1))
