@@ -964,10 +964,91 @@ __global__ void __launch_bounds__(256) head1x1_bwd_k(const float* __restrict__ g
     else atomicAdd(db + (threadIdx.x - KT * HD_C), t);
   }
 }
+// K = 16 classes (config 3): 256 weight-gradient accumulators do not fit one thread, so FOUR threads share a voxel, each owning a
+// quarter of the classes: 64 accumulators per thread, the partial dx of the four quarters is combined with two xor-shuffles and
+// every thread stores one float4 of it.  Same traffic as the small-K kernel: g, x read once (x from L1 for three of the four),
+// dx written once.
+__global__ void __launch_bounds__(256) head1x1_bwd16_k(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ w,
+                                                       float* __restrict__ dx, float* __restrict__ dw, float* __restrict__ db, long long rows) {
+  __shared__ float ws[16 * HD_C];
+  __shared__ float red[8][4 * 68];
+  for (int i = threadIdx.x; i < 16 * HD_C; i += 256) ws[i] = w[i];
+  __syncthreads();
+  const int q = threadIdx.x & 3;
+  float aw[4][HD_C], ab[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    ab[j] = 0.f;
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) aw[j][c] = 0.f;
+  }
+  const long long iters = (rows + (long long)gridDim.x * 64 - 1) / ((long long)gridDim.x * 64);
+  for (long long it = 0; it < iters; ++it) {   // uniform trip count: the shuffles below need the whole warp
+    const long long v = (it * gridDim.x + blockIdx.x) * 64 + (threadIdx.x >> 2);
+    const bool ok = v < rows;
+    float xv[HD_C], o[HD_C];
+    float4 gq = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ok) {
+      const float4* xp = reinterpret_cast<const float4*>(x + v * HD_C);
+#pragma unroll
+      for (int t = 0; t < 4; ++t) { const float4 u = xp[t]; xv[4 * t] = u.x; xv[4 * t + 1] = u.y; xv[4 * t + 2] = u.z; xv[4 * t + 3] = u.w; }
+      gq = *reinterpret_cast<const float4*>(g + v * 16 + 4 * q);
+    } else {
+#pragma unroll
+      for (int c = 0; c < HD_C; ++c) xv[c] = 0.f;
+    }
+    const float gv[4] = {gq.x, gq.y, gq.z, gq.w};
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) o[c] = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      ab[j] += gv[j];
+      const float* wr = ws + (4 * q + j) * HD_C;
+#pragma unroll
+      for (int c = 0; c < HD_C; ++c) { o[c] = fmaf(gv[j], wr[c], o[c]); aw[j][c] = fmaf(gv[j], xv[c], aw[j][c]); }
+    }
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) {
+      o[c] += __shfl_xor_sync(0xffffffffu, o[c], 1);
+      o[c] += __shfl_xor_sync(0xffffffffu, o[c], 2);
+    }
+    if (ok) {
+      float4 r;
+      r.x = q == 0 ? o[0] : (q == 1 ? o[4] : (q == 2 ? o[8] : o[12]));
+      r.y = q == 0 ? o[1] : (q == 1 ? o[5] : (q == 2 ? o[9] : o[13]));
+      r.z = q == 0 ? o[2] : (q == 1 ? o[6] : (q == 2 ? o[10] : o[14]));
+      r.w = q == 0 ? o[3] : (q == 1 ? o[7] : (q == 2 ? o[11] : o[15]));
+      *reinterpret_cast<float4*>(dx + v * HD_C + 4 * q) = r;
+    }
+  }
+  // lanes with equal q: xor-reduce over lane bits 2..4, then lanes 0..3 hold the warp totals of quarters 0..3
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+#pragma unroll
+    for (int c = 0; c < HD_C; ++c) {
+      float t = aw[j][c];
+      t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+      if (lane < 4) red[wid][lane * 68 + j * HD_C + c] = t;
+    }
+    float t = ab[j];
+    t += __shfl_xor_sync(0xffffffffu, t, 4); t += __shfl_xor_sync(0xffffffffu, t, 8); t += __shfl_xor_sync(0xffffffffu, t, 16);
+    if (lane < 4) red[wid][lane * 68 + 64 + j] = t;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 4 * 68; i += 256) {
+    float t = 0.f;
+    for (int wv = 0; wv < 8; ++wv) t += red[wv][i];
+    const int qq = i / 68, e = i % 68;
+    if (e < 64) atomicAdd(dw + (4 * qq + e / HD_C) * HD_C + (e % HD_C), t);
+    else atomicAdd(db + 4 * qq + (e - 64), t);
+  }
+}
 ICL_API int icl_head1x1_bwd(const float* g, const float* x, const float* w, float* dx, float* dw /* zeroed [K][16] */, float* db /* zeroed [K] */,
                             long long rows, int C, int K, void* stream) {
-  ICL_REQUIRE(C == HD_C && (K == 1 || K == 2 || K == 4), "head1x1_bwd: C=%d K=%d unsupported (C = 16, K in {1,2,4})", C, K);
+  ICL_REQUIRE(C == HD_C && (K == 1 || K == 2 || K == 4 || K == 16), "head1x1_bwd: C=%d K=%d unsupported (C = 16, K in {1,2,4,16})", C, K);
   const int grid = grid_for(rows, 256, 148 * 4);
+  if (K == 16) { head1x1_bwd16_k<<<grid_for(rows, 64, 148 * 4), 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows); ICL_LAUNCHED("head1x1_bwd"); }
   if (K == 1) head1x1_bwd_k<1><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);
   else if (K == 2) head1x1_bwd_k<2><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);
   else head1x1_bwd_k<4><<<grid, 256, 0, as_stream(stream)>>>(g, x, w, dx, dw, db, rows);

@@ -539,3 +539,33 @@ ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, floa
   planar_pw_finalize_k<<<cdiv(CO * (CI + 1), 128), 128, 0, as_stream(stream)>>>(ws, chunks, CO, CI, dw, db);
   ICL_LAUNCHED("planar_pw_wgrad");
 }
+
+// pointwise (1x1x1) conv on planar maps, forward and data gradient:  y[nb][o][s] = sum_i W[o*w_so + i*w_si] * x[nb][i][s] (+ bias[o]).
+// (data gradient = the same kernel with the weight strides swapped.)  One thread per (nb, s) position: CI coalesced loads, CO
+// coalesced stores, the CO x CI weights in shared memory — the maps stream through once (CI, CO <= 16).
+__global__ void __launch_bounds__(256) planar_pw_k(const float* __restrict__ x, const float* __restrict__ w, int w_so, int w_si,
+                                                   const float* __restrict__ bias, float* __restrict__ y, int NB, int CI, int CO, long long S) {
+  __shared__ float ws[16 * 16 + 16];
+  for (int i = threadIdx.x; i < CO * CI; i += 256) ws[i] = w[(i / CI) * w_so + (i % CI) * w_si];
+  for (int i = threadIdx.x; i < CO; i += 256) ws[256 + i] = bias ? bias[i] : 0.f;
+  __syncthreads();
+  const long long n = (long long)NB * S;
+  for (long long p = (long long)blockIdx.x * 256 + threadIdx.x; p < n; p += (long long)gridDim.x * 256) {
+    const long long nb = p / S, sp = p - nb * S;
+    float xv[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) xv[i] = i < CI ? x[(nb * CI + i) * S + sp] : 0.f;
+    for (int o = 0; o < CO; ++o) {
+      float a = ws[256 + o];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) if (i < CI) a = fmaf(ws[o * CI + i], xv[i], a);
+      y[(nb * CO + o) * S + sp] = a;
+    }
+  }
+}
+ICL_API int icl_planar_pw(const float* x, const float* w, int w_so, int w_si, const float* bias, float* y, int NB, int CI, int CO, long long S,
+                          void* stream) {
+  ICL_REQUIRE(CI >= 1 && CI <= 16 && CO >= 1 && CO <= 16, "planar_pw: CI=%d CO=%d unsupported (<= 16)", CI, CO);
+  planar_pw_k<<<grid_for((long long)NB * S, 256, 148 * 8), 256, 0, as_stream(stream)>>>(x, w, w_so, w_si, bias, y, NB, CI, CO, S);
+  ICL_LAUNCHED("planar_pw");
+}

@@ -301,8 +301,13 @@ class PlanarPointwiseFn(torch.autograd.Function):
         w2 = _c(w.detach()).reshape(w.shape[0], CI)
         CO = w2.shape[0]
         y = torch.empty((NB, CO) + tuple(x_.shape[2:]), dtype=torch.float32, device=x.device)
-        ops.sgemm(CO, S, CI, w2, CI, 1, x_, S, 1, y, S, 1, bias=None if b is None else b.detach(), bias_mode=2 if b is not None else 0,
-                  batch=NB, sA=0, sB=CI * S, sC=CO * S)
+        if CI <= 16 and CO <= 16:
+            b_ = None if b is None else _c(b.detach())
+            call("icl_planar_pw", P(x_), P(w2), c_int(CI), c_int(1), P(b_), P(y), c_int(NB), c_int(CI), c_int(CO), c_ll(S),
+                 mbytes=4e-6 * NB * S * (CI + CO), tag="NB%d %d->%d S%d" % (NB, CI, CO, S))
+        else:
+            ops.sgemm(CO, S, CI, w2, CI, 1, x_, S, 1, y, S, 1, bias=None if b is None else b.detach(), bias_mode=2 if b is not None else 0,
+                      batch=NB, sA=0, sB=CI * S, sC=CO * S)
         ctx.save_for_backward(x_, w2)
         ctx.has_bias, ctx.wshape = b is not None, w.shape
         return y
@@ -317,7 +322,11 @@ class PlanarPointwiseFn(torch.autograd.Function):
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x_)
-            ops.sgemm(CI, S, CO, w2, 1, CI, dy, S, 1, dx, S, 1, batch=NB, sA=0, sB=CO * S, sC=CI * S)
+            if CI <= 16 and CO <= 16:
+                call("icl_planar_pw", P(dy), P(w2), c_int(1), c_int(CI), P(None), P(dx), c_int(NB), c_int(CO), c_int(CI), c_ll(S),
+                     mbytes=4e-6 * NB * S * (CI + CO), tag="NB%d %d->%d S%d (dgrad)" % (NB, CO, CI, S))
+            else:
+                ops.sgemm(CI, S, CO, w2, 1, CI, dy, S, 1, dx, S, 1, batch=NB, sA=0, sB=CO * S, sC=CI * S)
         dw = torch.empty_like(w2)
         db = torch.empty((CO,), dtype=torch.float32, device=dy.device) if ctx.has_bias else None
         call("icl_planar_pw_wgrad", P(dy), P(x_), P(dw), P(db), c_int(NB), c_int(CO), c_int(CI), c_ll(S), P(ops.reduce_ws(x_.device)),

@@ -205,7 +205,7 @@ class Backbone3DFn(torch.autograd.Function):
             B, D, H, W, K = gf.shape
             rows, C1 = B * D * H * W, wf2.shape[1]
             d_up1d = torch.empty((B, D, H, W, C1), dtype=torch.float32, device=gf.device)
-            if C1 == 16 and K in (1, 2, 4):
+            if C1 == 16 and K in (1, 2, 4, 16):
                 dwf = torch.zeros((K, C1), dtype=torch.float32, device=gf.device)
                 dbf = torch.zeros((K,), dtype=torch.float32, device=gf.device)
                 ops.call("icl_head1x1_bwd", ops.P(gf), ops.P(rec["up1d"]), ops.P(wf2), ops.P(d_up1d), ops.P(dwf), ops.P(dbf), ops.c_ll(rows),

@@ -270,7 +270,7 @@ def sgemm(M, N, K, A, sam, sak, Bm, sbk, sbn, C, scm, scn, bias=None, bias_mode=
          gflop=2e-9 * M * N * K * batch, mbytes=4e-6 * batch * (M * K + K * N + M * N), tag="%dx%dx%d b%d" % (M, N, K, batch))
 
 
-BIGW_MIN_NUMEL = 1 << 22  # weights at least this large stream through the tcgen05 kernels (bigw_umma.cu)
+BIGW_MIN_NUMEL = 1 << 21  # weights at least this large (mlp2 at the 24^3 and 12^3 levels) stream through the tcgen05 kernels (bigw_umma.cu)
 
 
 def bigw_ok(M, N, K):

@@ -142,6 +142,8 @@ int icl_bn_relu_fwd(const float* x, const float* gamma, const float* beta, float
                     int CH, long long S, float eps, float momentum, double* ws, void* stream);
 int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums, float* dx, int NB,
                     int CH, long long S, double* ws, void* stream);
+int icl_planar_pw(const float* x, const float* w, int w_so, int w_si, const float* bias, float* y, int NB, int CI, int CO, long long S,
+                  void* stream);
 int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, float* ws, void* stream);
 
 /* ---- losses: CrossEntropyLoss + DiceLoss (utils/losses.py:195-231), AuxLoss3D (:254-271, trilinear
