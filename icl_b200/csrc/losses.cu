@@ -458,10 +458,10 @@ __global__ void __launch_bounds__(256, 2) class_stats_row_fwd_k(const float* __r
     if (lane == 0) red[wid][i] = sv;
   }
   __syncthreads();
-  if (threadIdx.x < 3 * K + 1) {
+  for (int i = threadIdx.x; i < 3 * K + 1; i += blockDim.x) {   // a block may have fewer threads than sums (short rows)
     double t = 0.0;
-    for (int w = 0; w < nw; ++w) t += (double)red[w][threadIdx.x];
-    atomicAdd(&sums[threadIdx.x], t);
+    for (int w = 0; w < nw; ++w) t += (double)red[w][i];
+    atomicAdd(&sums[i], t);
   }
 }
 

