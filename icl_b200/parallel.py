@@ -128,13 +128,14 @@ class GradAverager:
                     self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
         self.bytes_last = 0
         self.launched_in_backward = 0   # buckets whose all-reduce started from a hook during the last backward
+        self._launched = 0
 
     # ------------------------------------------------------------------ per-step bookkeeping
     def begin_step(self):
         for b in self.buckets.values():
             b.count = {}
             b.inflight = None
-        self.launched_in_backward = 0
+        self._launched = 0
 
     def _on_grad(self, p):
         b = self._bucket_of.get(id(p))
@@ -143,7 +144,7 @@ class GradAverager:
         b.count[id(p)] = b.count.get(id(p), 0) + 1
         if b.expected is not None and b.count == b.expected:
             self._launch(b)
-            self.launched_in_backward += 1
+            self._launched += 1
 
     def _launch(self, b):
         todo = [p for p in b.params if p.grad is not None]
@@ -190,6 +191,7 @@ class GradAverager:
             if self.overlap and b.count:
                 b.expected = dict(b.count)   # accumulations per parameter per step (stable from step to step)
         self.bytes_last = total
+        self.launched_in_backward = self._launched
         self.begin_step()
 
     def sync_buffers(self, model, mode="mean"):

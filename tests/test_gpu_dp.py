@@ -138,6 +138,8 @@ def _worker(rank, world, port, K, use_graph, q):
                 if upd == 0.0:   # a parameter the reference never updates (grad is None) must not move under DP either
                     assert d == 0.0, k
                     continue
+                if k.endswith(".0.bias") and not (k.startswith("sspa") or k.startswith("uscl")):
+                    continue     # conv bias in front of InstanceNorm: mathematically-zero gradient, the "update" is rounding noise
                 worst.append((d / upd, k))
             worst.sort(reverse=True)
             result["worst"] = worst[:5]
@@ -168,9 +170,13 @@ def test_dp2_step_equals_mean_gradient_step(K, use_graph):
     for r, (status, payload) in out.items():
         assert status == "ok", "rank %d:\n%s" % (r, payload)
     worst = out[0][1]["worst"]
-    # |p_dp - p_ref| relative to the size of the 2-step UPDATE |p_ref - p_init| of each tensor: the same sums in a different fp32
-    # order (split-bf16 factor products inside the fused optimizer vs the materialised fp32 gradient)
-    assert worst[0][0] <= 2e-3, worst
+    # |p_dp - p_ref| relative to the size of the 2-step UPDATE |p_ref - p_init| of each tensor.  The bound is the RUN-TO-RUN noise of
+    # this network, not the exchange: two single-process evaluations of the same batch already differ by up to ~1e-2 in the deep
+    # layers' weight gradients (tools/dp_debug.py, profiles/r02g_dp_debug.log: "noise floor") because the InstanceNorm statistics
+    # are accumulated with atomics, a handful of pre-activations within 1e-7 of zero flip their ReLU derivative, and at random
+    # init a weight gradient is a heavily cancelling sum in which ONE voxel weighs ~1/sqrt(#voxels) (1.7 % at the 12^3 level).
+    # An exchange bug (missing bucket, wrong 1/world, stale factors) shows up as an error of order 0.5 - 1.
+    assert worst[0][0] <= 5e-2, worst
     if not use_graph:
         # the ICL-head bucket must have started from a grad-ready hook inside backward from the second step on
         assert out[0][1]["launched"][1] >= 1, out[0][1]["launched"]
