@@ -334,7 +334,7 @@ __global__ void __launch_bounds__(256) class_stats_bwd_k(const float* __restrict
 // the old two-stage path wrote), and trilinear_adjoint_k finishes the y / z adjoint on that reduced tensor.
 // ------------------------------------------------------------------------------------------
 #define ROW_MAXX 256
-#define ROW_TABW 129   // rx <= X / 2 <= 128 (+1: odd stride, conflict-free columns)
+#define ROW_MAXRX 128   // rx <= X / 2
 
 template <int KT>
 __device__ __forceinline__ void load_vec(const float* __restrict__ p, int K, float* L) {
@@ -365,9 +365,10 @@ __device__ __forceinline__ void store_vec(float* __restrict__ p, int K, const fl
   }
 }
 
-// tab[k][cx] = z/y-interpolated coarse row for fine row (z, y) of sample b.  All threads of the block; caller syncs.
+// One WARP owns a row (no block-wide barriers inside the row loop; 8 rows in flight per block).
+// tab[k][cx] (row stride tw = rx + 1) = z/y-interpolated coarse row for fine row (z, y) of sample b.  Caller __syncwarp()s.
 template <int KT>
-__device__ __forceinline__ void row_table(const float* __restrict__ src, const SrcGeom& g, int K, int b, int z, int y, float* tab) {
+__device__ __forceinline__ void row_table(const float* __restrict__ src, const SrcGeom& g, int K, int b, int z, int y, float* tab, int tw, int lane) {
   int z0, z1, y0, y1; float lz, ly;
   lin_src(z, g.sz, g.rz, z0, z1, lz); lin_src(y, g.sy, g.ry, y0, y1, ly);
   const float w00 = (1.f - lz) * (1.f - ly), w01 = (1.f - lz) * ly, w10 = lz * (1.f - ly), w11 = lz * ly;
@@ -375,17 +376,17 @@ __device__ __forceinline__ void row_table(const float* __restrict__ src, const S
   const long long r00 = ((long long)z0 * g.ry + y0) * g.rx, r01 = ((long long)z0 * g.ry + y1) * g.rx;
   const long long r10 = ((long long)z1 * g.ry + y0) * g.rx, r11 = ((long long)z1 * g.ry + y1) * g.rx;
   const int n = K * g.rx;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+  for (int i = lane; i < n; i += 32) {
     int k, cx; long long st; const float* p;
     if (g.planar) { k = i / g.rx; cx = i - k * g.rx; p = src + ((long long)b * K + k) * Sr + cx; st = 1; }
     else { cx = i / K; k = i - cx * K; p = src + (long long)b * Sr * K + (long long)cx * K + k; st = K; }
-    tab[k * ROW_TABW + cx] = w00 * p[r00 * st] + w01 * p[r01 * st] + w10 * p[r10 * st] + w11 * p[r11 * st];
+    tab[k * tw + cx] = w00 * p[r00 * st] + w01 * p[r01 * st] + w10 * p[r10 * st] + w11 * p[r11 * st];
   }
 }
 
 template <int KT>
 __device__ __forceinline__ void row_logits(const float* __restrict__ src, const SrcGeom& g, bool direct, int K, long long vox_in_batch, int b,
-                                           int x, const float* tab, float* L) {
+                                           int x, const float* tab, int tw, float* L) {
   if (direct) {
     const long long S = (long long)g.Z * g.Y * g.X;
     if (g.planar) {
@@ -398,34 +399,37 @@ __device__ __forceinline__ void row_logits(const float* __restrict__ src, const 
     int x0, x1; float lx;
     lin_src(x, g.sx, g.rx, x0, x1, lx);
 #pragma unroll
-    for (int k = 0; k < KT; ++k) if (k < K) L[k] = (1.f - lx) * tab[k * ROW_TABW + x0] + lx * tab[k * ROW_TABW + x1];
+    for (int k = 0; k < KT; ++k) if (k < K) L[k] = (1.f - lx) * tab[k * tw + x0] + lx * tab[k * tw + x1];
   }
 }
 
 template <int KT>
 __global__ void __launch_bounds__(256, 2) class_stats_row_fwd_k(const float* __restrict__ src, SrcGeom g, int B, int K,
-                                                             const long long* __restrict__ labels, const float* __restrict__ tgt,
-                                                             int is_prob, double* __restrict__ sums) {
-  __shared__ float tab[KT * ROW_TABW];
+                                                                const long long* __restrict__ labels, const float* __restrict__ tgt,
+                                                                int is_prob, double* __restrict__ sums) {
+  extern __shared__ float dsm[];   // per warp: tab[KT][rx + 1]
   __shared__ float red[8][3 * KT + 1];
   float acc[3 * KT + 1];
 #pragma unroll
   for (int i = 0; i < 3 * KT + 1; ++i) acc[i] = 0.f;
   const bool direct = g.rz == g.Z && g.ry == g.Y && g.rx == g.X;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  const int tw = g.rx + 1;
+  float* tab = dsm + (size_t)wid * KT * tw;
   const long long rows = (long long)B * g.Z * g.Y;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+  for (long long row = (long long)blockIdx.x * nw + wid; row < rows; row += (long long)gridDim.x * nw) {
     const int b = (int)(row / ((long long)g.Z * g.Y));
     const int zy = (int)(row - (long long)b * g.Z * g.Y);
     const int z = zy / g.Y, y = zy - z * g.Y;
     if (!direct) {
-      __syncthreads();   // the previous row's readers are done with the table
-      row_table<KT>(src, g, K, b, z, y, tab);
-      __syncthreads();
+      __syncwarp();   // the previous row's readers are done with the table
+      row_table<KT>(src, g, K, b, z, y, tab, tw, lane);
+      __syncwarp();
     }
-    for (int x = threadIdx.x; x < g.X; x += blockDim.x) {
+    for (int x = lane; x < g.X; x += 32) {
       const long long v = (long long)zy * g.X + x, i = row * g.X + x;
       float L[KT];
-      row_logits<KT>(src, g, direct, K, v, b, x, tab, L);
+      row_logits<KT>(src, g, direct, K, v, b, x, tab, tw, L);
       float mx, lse;
       if (labels) {
         const int lab = (int)labels[i];
@@ -451,14 +455,13 @@ __global__ void __launch_bounds__(256, 2) class_stats_row_fwd_k(const float* __r
       }
     }
   }
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
   for (int i = 0; i < 3 * KT + 1; ++i) {
     const float sv = warp_sum(acc[i]);
     if (lane == 0) red[wid][i] = sv;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 3 * K + 1; i += blockDim.x) {   // a block may have fewer threads than sums (short rows)
+  for (int i = threadIdx.x; i < 3 * K + 1; i += blockDim.x) {
     double t = 0.0;
     for (int w = 0; w < nw; ++w) t += (double)red[w][i];
     atomicAdd(&sums[i], t);
@@ -497,14 +500,13 @@ __device__ __forceinline__ void dlogits_from(float* L, int K, long long i, const
 // direct sources: dsrc (layout of src) = per-voxel gradient.  Interpolated sources: xred[b][k][z][y][cx] = x-adjoint of the row.
 template <int KT>
 __global__ void __launch_bounds__(256, 2) class_stats_row_bwd_k(const float* __restrict__ src, SrcGeom g, int B, int K,
-                                                             const long long* __restrict__ labels, const float* __restrict__ tgt,
-                                                             int is_prob, const float* __restrict__ class_w, const double* __restrict__ sums,
-                                                             const float* __restrict__ g_ce, const float* __restrict__ g_dice, float w_ce,
-                                                             float w_dice, float* __restrict__ dsrc, float* __restrict__ xred) {
+                                                                const long long* __restrict__ labels, const float* __restrict__ tgt,
+                                                                int is_prob, const float* __restrict__ class_w, const double* __restrict__ sums,
+                                                                const float* __restrict__ g_ce, const float* __restrict__ g_dice, float w_ce,
+                                                                float w_dice, float* __restrict__ dsrc, float* __restrict__ xred) {
   __shared__ float cA[KT], cB[KT];
   __shared__ float cCE;
-  __shared__ float tab[KT * ROW_TABW];
-  extern __shared__ float sdl[];   // [KT][X + 1] per-voxel gradients of the current row (interpolated sources only)
+  extern __shared__ float dsm[];   // per warp (interpolated sources only): tab[KT][rx + 1], then sdl[KT][X + 1]
   const bool direct = g.rz == g.Z && g.ry == g.Y && g.rx == g.X;
   if (threadIdx.x < K) {
     const int k = threadIdx.x;
@@ -515,21 +517,24 @@ __global__ void __launch_bounds__(256, 2) class_stats_row_bwd_k(const float* __r
   }
   if (threadIdx.x == 0) cCE = (g_ce && labels && !is_prob) ? g_ce[0] * w_ce / (float)((double)B * g.Z * g.Y * g.X) : 0.f;
   __syncthreads();
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
   const long long rows = (long long)B * g.Z * g.Y, S = (long long)g.Z * g.Y * g.X;
-  const int XS = g.X + 1, fx = direct ? 1 : g.X / g.rx;
-  for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+  const int tw = g.rx + 1, XS = g.X + 1, fx = direct ? 1 : g.X / g.rx;
+  float* tab = dsm + (size_t)wid * KT * (tw + XS);
+  float* sdl = tab + KT * tw;
+  for (long long row = (long long)blockIdx.x * nw + wid; row < rows; row += (long long)gridDim.x * nw) {
     const int b = (int)(row / ((long long)g.Z * g.Y));
     const int zy = (int)(row - (long long)b * g.Z * g.Y);
     const int z = zy / g.Y, y = zy - z * g.Y;
     if (!direct) {
-      __syncthreads();   // previous row: table readers and sdl readers are done
-      row_table<KT>(src, g, K, b, z, y, tab);
-      __syncthreads();
+      __syncwarp();   // previous row: table readers and sdl readers are done
+      row_table<KT>(src, g, K, b, z, y, tab, tw, lane);
+      __syncwarp();
     }
-    for (int x = threadIdx.x; x < g.X; x += blockDim.x) {
+    for (int x = lane; x < g.X; x += 32) {
       const long long v = (long long)zy * g.X + x, i = row * g.X + x;
       float L[KT], dl[KT];
-      row_logits<KT>(src, g, direct, K, v, b, x, tab, L);
+      row_logits<KT>(src, g, direct, K, v, b, x, tab, tw, L);
       dlogits_from<KT>(L, K, i, labels, tgt, is_prob, cA, cB, cCE, dl);
       if (direct) {
         if (g.planar) {
@@ -544,10 +549,10 @@ __global__ void __launch_bounds__(256, 2) class_stats_row_bwd_k(const float* __r
       }
     }
     if (!direct) {
-      __syncthreads();
+      __syncwarp();
       // x-adjoint: coarse column cx collects the fine columns whose interpolation footprint touches it
       const int n = K * g.rx;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      for (int i = lane; i < n; i += 32) {
         const int k = i / g.rx, cx = i - k * g.rx;
         const int x0 = max(0, cx * fx - fx / 2 - 1), x1 = min(g.X - 1, cx * fx + (3 * fx) / 2);
         float a = 0.f;
@@ -561,6 +566,38 @@ __global__ void __launch_bounds__(256, 2) class_stats_row_bwd_k(const float* __r
       }
     }
   }
+}
+
+// y / z adjoint of the trilinear interpolation on the x-reduced gradient xr[B*K][Z][Y][rx], small footprints: one THREAD per coarse
+// cell (consecutive threads = consecutive cx: coalesced rows of rx floats), (2 fy + 2) x (2 fz + 2) taps each.
+__global__ void __launch_bounds__(256) yz_adjoint_cell_k(const float* __restrict__ xr, SrcGeom g, int K, float* __restrict__ dsrc, long long cells) {
+  const long long cell = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (cell >= cells) return;
+  long long c = cell;
+  const int cx = (int)(c % g.rx); c /= g.rx;
+  const int cy = (int)(c % g.ry); c /= g.ry;
+  const int cz = (int)(c % g.rz); const int bk = (int)(c / g.rz);
+  const int fz = g.Z / g.rz, fy = g.Y / g.ry;
+  const int z0 = max(0, cz * fz - fz / 2 - 1), z1 = min(g.Z - 1, cz * fz + (3 * fz) / 2);
+  const int y0 = max(0, cy * fy - fy / 2 - 1), y1 = min(g.Y - 1, cy * fy + (3 * fy) / 2);
+  const float* base = xr + (long long)bk * g.Z * g.Y * g.rx + cx;
+  float acc = 0.f;
+  for (int z = z0; z <= z1; ++z) {
+    int i0, i1; float l1;
+    lin_src(z, g.sz, g.rz, i0, i1, l1);
+    const float wz = (i0 == cz ? 1.f - l1 : 0.f) + (i1 == cz ? l1 : 0.f);
+    if (wz == 0.f) continue;
+    float a = 0.f;
+    for (int y = y0; y <= y1; ++y) {
+      lin_src(y, g.sy, g.ry, i0, i1, l1);
+      const float wy = (i0 == cy ? 1.f - l1 : 0.f) + (i1 == cy ? l1 : 0.f);
+      a = fmaf(wy, base[((long long)z * g.Y + y) * g.rx], a);
+    }
+    acc = fmaf(wz, a, acc);
+  }
+  const long long Sr = (long long)g.rz * g.ry * g.rx, sp = ((long long)cz * g.ry + cy) * g.rx + cx;
+  const int b = bk / K, k = bk % K;
+  if (g.planar) dsrc[((long long)b * K + k) * Sr + sp] = acc; else dsrc[((long long)b * Sr + sp) * K + k] = acc;
 }
 
 static int make_geom(SrcGeom& g, int planar, int rz, int ry, int rx, int Z, int Y, int X) {
@@ -580,7 +617,14 @@ static int make_geom(SrcGeom& g, int planar, int rz, int ry, int rx, int Z, int 
 static inline bool row_path_ok(bool direct, int rx, int X) {
   const char* e = getenv("ICL_DISABLE_ROW_LOSS");
   if (e && e[0] == '1') return false;
-  return X <= ROW_MAXX && (direct || (rx <= ROW_TABW - 1 && 2 * rx <= X));
+  return X <= ROW_MAXX && (direct || (rx <= ROW_MAXRX && 2 * rx <= X));
+}
+
+// warps (= rows in flight) per block of the row kernels: up to 8, limited by their per-warp shared-memory staging
+static inline int row_warps(size_t per_warp_bytes) {
+  int w = 8;
+  while (w > 1 && per_warp_bytes * w > 90 * 1024) w >>= 1;
+  return w;
 }
 
 #define DISPATCH_K(K, CALL)                                      \
@@ -596,10 +640,14 @@ ICL_API int icl_class_stats_fwd(const float* src, int planar, int rz, int ry, in
   const long long total = (long long)B * Z * Y * X;
   const bool direct = rz == Z && ry == Y && rx == X;
   if (row_path_ok(direct, rx, X)) {
-    const int threads = X >= 256 ? 256 : ((X + 31) / 32) * 32;
     const long long rows = (long long)B * Z * Y;
-    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
-#define CALL(KT) class_stats_row_fwd_k<KT><<<grid, threads, 0, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, sums)
+#define CALL(KT) do { \
+      const size_t per_warp = direct ? 0 : (size_t)KT * (rx + 1) * sizeof(float); \
+      const int warps = row_warps(per_warp); \
+      static bool cfg = false; \
+      if (!cfg) { cudaFuncSetAttribute(class_stats_row_fwd_k<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; } \
+      const int grid = (int)(cdiv(rows, warps) < 148 * 2 ? cdiv(rows, warps) : 148 * 2); \
+      class_stats_row_fwd_k<KT><<<grid, warps * 32, per_warp * warps, as_stream(stream)>>>(src, g, B, K, labels, tgt, is_prob, sums); } while (0)
     DISPATCH_K(K, CALL)
 #undef CALL
   } else {
@@ -622,25 +670,31 @@ ICL_API int icl_class_stats_bwd(const float* src, int planar, int rz, int ry, in
   const long long blocks = (long long)B * cdiv(Z, BT_Z) * cdiv(Y, BT_Y) * cdiv(X, BT_X);
   const bool direct = rz == Z && ry == Y && rx == X;
   if (row_path_ok(direct, rx, X) && (direct || (workspace && Z % rz == 0 && Y % ry == 0 && X % rx == 0))) {
-    const int threads = X >= 256 ? 256 : ((X + 31) / 32) * 32;
     const long long rows = (long long)B * Z * Y;
-    const int grid = (int)(rows < 148 * 8 ? rows : 148 * 8);
-    const size_t smem = direct ? 0 : (size_t)16 * (X + 1) * sizeof(float);
-#define CALL(KT) class_stats_row_bwd_k<KT><<<grid, threads, direct ? 0 : (size_t)KT * (X + 1) * sizeof(float), as_stream(stream)>>>( \
-      src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, workspace)
+#define CALL(KT) do { \
+      const size_t per_warp = direct ? 0 : (size_t)KT * (rx + 1 + X + 1) * sizeof(float); \
+      const int warps = row_warps(per_warp); \
+      static bool cfg = false; \
+      if (!cfg) { cudaFuncSetAttribute(class_stats_row_bwd_k<KT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); cfg = true; } \
+      const int grid = (int)(cdiv(rows, warps) < 148 * 2 ? cdiv(rows, warps) : 148 * 2); \
+      class_stats_row_bwd_k<KT><<<grid, warps * 32, per_warp * warps, as_stream(stream)>>>( \
+          src, g, B, K, labels, tgt, is_prob, class_w, sums, g_ce, g_dice, w_ce, w_dice, dsrc, workspace); } while (0)
     DISPATCH_K(K, CALL)
 #undef CALL
-    (void)smem;
     if (!direct) {
       icl_count_launch(1);
       // y / z adjoint on the x-reduced gradient [B][K][Z][Y][rx]: the same gather kernel with an untouched x axis
       SrcGeom g2;
       if (make_geom(g2, planar, rz, ry, rx, Z, Y, rx)) return -1;
-      const long long foot = 4LL * (Z / rz) * (Y / ry) * 3;
-      const int G = foot >= 4096 ? 256 : 32;
       const long long cells = (long long)B * K * rz * ry * rx;
-      const long long nb = (cells + (256 / G) - 1) / (256 / G);
-      trilinear_adjoint_k<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(workspace, g2, K, dsrc, G, cells);
+      const long long foot = (2LL * (Z / rz) + 2) * (2LL * (Y / ry) + 2);
+      if (foot <= 400 && cells >= 148 * 256) {
+        yz_adjoint_cell_k<<<(unsigned)cdiv(cells, 256), 256, 0, as_stream(stream)>>>(workspace, g2, K, dsrc, cells);
+      } else {
+        const int G = 4 * foot >= 4096 ? 256 : 32;
+        const long long nb = (cells + (256 / G) - 1) / (256 / G);
+        trilinear_adjoint_k<<<(unsigned)nb, 256, 0, as_stream(stream)>>>(workspace, g2, K, dsrc, G, cells);
+      }
     }
     ICL_LAUNCHED("class_stats_bwd");
   }

@@ -40,20 +40,21 @@ class _Act:
 
 
 class _Half:
-    __slots__ = ("srcs", "w", "y", "mr", "out", "umma")
+    __slots__ = ("srcs", "w", "y", "mr", "out", "umma", "owner")
 
 
-def _half_fwd(srcs, w, b):
-    """conv3x3x3(+bias) -> InstanceNorm -> ReLU on the virtual concat of `srcs` (list of _Act)."""
+def _half_fwd(srcs, w, b, owner=None):
+    """conv3x3x3(+bias) -> InstanceNorm -> ReLU on the virtual concat of `srcs` (list of _Act).  `owner`: the nn.Parameter `w` was
+    detached from (guards the packed-operand cache)."""
     cins = [s.C for s in srcs]
     cout = w.shape[0]
     B, D, H, W, _ = srcs[0].shape
     stats = torch.zeros((B, cout, 2), dtype=torch.float64, device=w.device)
     h = _Half()
-    h.srcs, h.w = srcs, w
+    h.srcs, h.w, h.owner = srcs, w, owner
     h.umma = ops.umma_ok(cins, cout) and all(s.pk is not None for s in srcs)
     if h.umma:
-        h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma(w, False, D), b, cout, B, D, H, W, stats)
+        h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma_cached(w, False, D, owner), b, cout, B, D, H, W, stats)
     elif ops.stem_ok(cins, cout):
         h.y = ops.conv3d_stem_fwd(srcs[0].f32, w, b, B, D, H, W, stats)
     else:
@@ -85,7 +86,7 @@ def _half_bwd(h, dA, need_dx):
         return dw, db, None
     cin_total = sum(cins)
     if dgrad_umma:
-        wp = ops.pack_w_umma(h.w, True, D)
+        wp = ops.pack_w_umma_cached(h.w, True, D, h.owner)
         if len(cins) == 2:
             d0, d1 = ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W, split=cins[0])
             return dw, db, [d0, d1]
@@ -96,9 +97,9 @@ def _half_bwd(h, dA, need_dx):
     return dw, db, [dx]
 
 
-def _block_fwd(srcs, p):
-    h1 = _half_fwd(srcs, p[0], p[1])
-    h2 = _half_fwd([h1.out], p[2], p[3])
+def _block_fwd(srcs, p, owners=(None, None)):
+    h1 = _half_fwd(srcs, p[0], p[1], owners[0])
+    h2 = _half_fwd([h1.out], p[2], p[3], owners[1])
     return (h1, h2)
 
 
@@ -129,6 +130,7 @@ class Backbone3DFn(torch.autograd.Function):
         ctx.set_materialize_grads(False)
         p = [t.detach() for t in params]
         blk = {name: p[4 * i:4 * i + 4] for i, name in enumerate(PARAM_BLOCKS)}
+        own = {name: (params[4 * i], params[4 * i + 2]) for i, name in enumerate(PARAM_BLOCKS)}   # weight Parameters of conv1 / conv2
         wf, bf = p[36], p[37]
         x_ = ops.to_ndhwc(x.detach())
         B, D, H, W, Cin = x_.shape
@@ -143,12 +145,12 @@ class Backbone3DFn(torch.autograd.Function):
         a0 = _Act(x_, ops.pack_pk(x_) if ops.pk_ok(Cin) else None)
         enc = a0
         for i, name in enumerate(["conv1", "conv2", "conv3", "conv4"]):
-            rec[name] = _block_fwd([enc], blk[name])
+            rec[name] = _block_fwd([enc], blk[name], own[name])
             out = rec[name][1].out
             pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C), want_f32=not lean)
             rec["pool%d" % (i + 1)] = idx
             enc = _Act(pooled, ppk, (B, out.shape[1] // 2, out.shape[2] // 2, out.shape[3] // 2, out.C))
-        rec["center"] = _block_fwd([enc], blk["center"])
+        rec["center"] = _block_fwd([enc], blk["center"], own["center"])
         center = rec["center"][1].out
         if drop_cfg is not None:
             pdrop, m1, m2, s1, s2 = drop_cfg
@@ -161,7 +163,7 @@ class Backbone3DFn(torch.autograd.Function):
                            ("up_concat1.conv", "conv1")):
             up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
             cs = coarse.shape
-            rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name])
+            rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name])
             coarse = rec[name][1].out
         up1 = coarse
         up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32

@@ -109,6 +109,32 @@ def pack_w_umma(w, dgrad, D=0):
     return wp
 
 
+# Packed tensor-core weight operands are cached per weight tensor: one pack per weight per optimizer step instead of one per conv
+# call (labeled + unlabeled forward, the data-gradient operand in both backward passes; every sliding window at inference).
+# An entry is valid while the owning tensor is alive, its version counter is unchanged (torch in-place updates, load_state_dict) and
+# no icl_b200 optimizer step has run since (our SGD kernels update parameters through raw pointers: weights_changed()).
+_WPACK = {}
+
+
+def weights_changed():
+    _WPACK.clear()
+
+
+def pack_w_umma_cached(w, dgrad, D=0, owner=None):
+    """pack_w_umma with the cache above.  `owner`: the tensor whose identity / version guards the entry (the nn.Parameter `w` was
+    detached from); without it nothing is cached."""
+    if owner is None or os.environ.get("ICL_DISABLE_WPACK_CACHE") == "1":
+        return pack_w_umma(w, dgrad, D)
+    import weakref
+    key = (id(owner), bool(dgrad), int(D), planes())
+    hit = _WPACK.get(key)
+    if hit is not None and hit[0]() is owner and hit[1] == owner._version and hit[2] == w.data_ptr():
+        return hit[3]
+    wp = pack_w_umma(w, dgrad, D)
+    _WPACK[key] = (weakref.ref(owner), owner._version, w.data_ptr(), wp)
+    return wp
+
+
 def repack_w_f32(w, dgrad):
     cout, cin = w.shape[0], w.shape[1]
     wp = torch.empty(27 * cin * cout, dtype=torch.float32, device=w.device)

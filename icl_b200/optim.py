@@ -156,4 +156,5 @@ class SGD(torch.optim.Optimizer):
             with torch.cuda.device(dev):
                 call("icl_sgd_multi", P(tab), P(ct), P(co), c_int(ct.numel()), P(lr), c_f(group["momentum"]), c_f(group["weight_decay"]),
                      c_int(0), mbytes=20e-6 * sum(r[3] for r in rows))
+        ops.weights_changed()   # packed tensor-core weight operands are stale now (the kernels wrote through raw pointers)
         return loss
