@@ -431,7 +431,7 @@ __global__ void bn_bwd_finalize_k(const double* __restrict__ part, int chunks, f
   double a = 0.0, q = 0.0;
   for (int i = lane; i < chunks; i += 32) { a += part[((long long)c * chunks + i) * 2]; q += part[((long long)c * chunks + i) * 2 + 1]; }
   a = warp_sum_d(a); q = warp_sum_d(q);
-  if (lane == 0) { sums[2 * c] = (float)a; sums[2 * c + 1] = (float)q; }
+  if (lane == 0) { sums[c] = (float)a; sums[gridDim.x + c] = (float)q; }   // [2][CH]: row 0 = dbeta, row 1 = dgamma
 }
 __global__ void bn_relu_apply_k(const float* __restrict__ x, const float* __restrict__ mean_rstd, const float* __restrict__ g,
                                 const float* __restrict__ b, float* __restrict__ y, int CH, long long S, long long total) {
@@ -462,10 +462,10 @@ __global__ void bn_relu_bwd_apply_k(const float* __restrict__ dy, const float* _
     const float m = mean_rstd[2 * c], r = mean_rstd[2 * c + 1];
     const float gg = y[i] > 0.f ? dy[i] : 0.f;
     const float xh = (x[i] - m) * r;
-    dx[i] = g[c] * r * (gg - sums[2 * c] * inv_n - xh * sums[2 * c + 1] * inv_n);
+    dx[i] = g[c] * r * (gg - sums[c] * inv_n - xh * sums[CH + c] * inv_n);
   }
 }
-ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums /*[CH,2]: dbeta,dgamma*/,
+ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, const float* mean_rstd, const float* gamma, float* sums /*[2][CH]: dbeta row, dgamma row*/,
                             float* dx, int NB, int CH, long long S, double* ws, void* stream) {
   ICL_REQUIRE(ws != nullptr, "bn_relu_bwd: workspace of icl_reduce_workspace_bytes() bytes required");
   const int chunks = red_chunks((long long)NB * S, 4096);

@@ -91,8 +91,8 @@ class LayerNormFn(torch.autograd.Function):
         g = _c(dy).reshape(-1, C)
         dx = torch.empty_like(x2) if ctx.needs_input_grad[0] else None
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
-        dw = torch.zeros((C,), dtype=torch.float32, device=g.device) if want_w else None
-        db = torch.zeros((C,), dtype=torch.float32, device=g.device) if want_w else None
+        dw = ops.zeros((C,), torch.float32, g.device) if want_w else None
+        db = ops.zeros((C,), torch.float32, g.device) if want_w else None
         call("icl_layernorm_bwd", P(g), P(x2), P(w), P(mr), P(dx), P(dw), P(db), c_ll(x2.shape[0]), c_int(C))
         return (dx.reshape(ctx.xshape) if dx is not None else None), dw, db, None
 
@@ -276,17 +276,27 @@ class BnReluFn(torch.autograd.Function):
     def backward(ctx, dy):
         x_, y, mr, gamma = ctx.saved_tensors
         NB, CH, S = ctx.dims
-        sums = torch.empty((CH, 2), dtype=torch.float32, device=x_.device)
+        sums = torch.empty((2, CH), dtype=torch.float32, device=x_.device)   # rows: dbeta, dgamma
         dx = torch.empty_like(x_)
         dy_c = _c(dy)
         call("icl_bn_relu_bwd", P(dy_c), P(x_), P(y), P(mr), P(gamma), P(sums), P(dx), c_int(NB), c_int(CH), c_ll(S), P(ops.reduce_ws(x_.device)),
              mbytes=28e-6 * x_.numel(), tag="NB%d CH%d S%d" % (NB, CH, S))
-        return dx, sums[:, 1].contiguous(), sums[:, 0].contiguous(), None, None, None, None, None
+        return dx, sums[1], sums[0], None, None, None, None, None
+
+
+_PENDING_NBT = []
+
+
+def flush_batch_counters():
+    """num_batches_tracked += 1 of every BatchNorm that ran since the last flush, as ONE multi-tensor add (18 per training step)."""
+    if _PENDING_NBT:
+        torch._foreach_add_(list(_PENDING_NBT), 1)
+        del _PENDING_NBT[:]
 
 
 def bn_relu(x, bn, training):
     if training and bn.num_batches_tracked is not None:
-        bn.num_batches_tracked += 1
+        _PENDING_NBT.append(bn.num_batches_tracked)
     return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps)
 
 

@@ -88,7 +88,7 @@ class Conv2dBnActFn(torch.autograd.Function):
         N, H, W, _ = xs[0].shape
         cout = w.shape[0]
         w3 = _w3d(w)
-        stats = torch.zeros((1, cout, 2), dtype=torch.float64, device=w.device)
+        stats = ops.zeros((1, cout, 2), torch.float64, w.device)
         y, pks = _conv_fwd(xs, w3, b.detach(), N, H, W, stats)
         S = N * H * W
         if training:
@@ -117,11 +117,11 @@ class Conv2dBnActFn(torch.autograd.Function):
             raise RuntimeError("icl_b200 Conv2dBnActFn: backward through eval-mode BatchNorm is not on the reference's path")
         dA_ = _nhwc(dA)
         S = N * H * W
-        red = torch.zeros((1, cout, 2), dtype=torch.float64, device=y.device)
+        red = ops.zeros((1, cout, 2), torch.float64, y.device)
         want_pk = cout % 16 == 0
         dY = torch.empty_like(y)
         pk = ops.empty_pk(1, cout, N, H, W, y.device) if want_pk else None
-        db = torch.zeros((cout,), dtype=torch.float32, device=y.device) if cout % 8 == 0 else None
+        db = ops.zeros((cout,), torch.float32, y.device) if cout % 8 == 0 else None
         call("icl_normact_bwd", P(dA_), P(y), P(mr), P(gamma), P(beta), c_f(ctx.slope), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0),
              P(db), c_int(1), c_int(cout), c_ll(S))
         dgamma, dbeta = red[0, :, 1].float(), red[0, :, 0].float()

@@ -49,7 +49,7 @@ def _half_fwd(srcs, w, b, owner=None):
     cins = [s.C for s in srcs]
     cout = w.shape[0]
     B, D, H, W, _ = srcs[0].shape
-    stats = torch.zeros((B, cout, 2), dtype=torch.float64, device=w.device)
+    stats = ops.zeros((B, cout, 2), torch.float64, w.device)
     h = _Half()
     h.srcs, h.w, h.owner = srcs, w, owner
     h.umma = ops.umma_ok(cins, cout) and all(s.pk is not None for s in srcs)
@@ -208,8 +208,8 @@ class Backbone3DFn(torch.autograd.Function):
             rows, C1 = B * D * H * W, wf2.shape[1]
             d_up1d = torch.empty((B, D, H, W, C1), dtype=torch.float32, device=gf.device)
             if C1 == 16 and K in (1, 2, 4, 16):
-                dwf = torch.zeros((K, C1), dtype=torch.float32, device=gf.device)
-                dbf = torch.zeros((K,), dtype=torch.float32, device=gf.device)
+                dwf = ops.zeros((K, C1), torch.float32, gf.device)
+                dbf = ops.zeros((K,), torch.float32, gf.device)
                 ops.call("icl_head1x1_bwd", ops.P(gf), ops.P(rec["up1d"]), ops.P(wf2), ops.P(d_up1d), ops.P(dwf), ops.P(dbf), ops.c_ll(rows),
                          ops.c_int(16), ops.c_int(K), mbytes=4e-6 * rows * (32 + K))
             else:

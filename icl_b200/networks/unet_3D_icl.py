@@ -25,8 +25,26 @@ class DropPath(nn.Module):
             return None
         if self._queue:
             return self._queue.pop(0).to(device=device, dtype=torch.float32).reshape(B).contiguous()
-        keep = 1.0 - self.drop_prob
-        return torch.empty((B,), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)
+        return _droppath_draw(1.0 - self.drop_prob, B, device)
+
+
+# DropPath scales come from a pool drawn with ONE bernoulli_ + ONE div_ (instead of a pair of tiny kernels per draw: 36 draws per
+# training step).  The pool holds as many rows as the previous refill period consumed (at least 16); it is refilled when exhausted
+# or when CUDA-graph capture begins / ends (the draw must be a node of the graph that consumes it).
+_DP_POOL = {}
+
+
+def _droppath_draw(keep, B, device):
+    capturing = torch.cuda.is_current_stream_capturing() if device.type == "cuda" else False
+    key = (str(device), B, float(keep))
+    st = _DP_POOL.get(key)
+    if st is None or st["i"] >= st["pool"].shape[0] or st["cap"] != capturing:
+        rows = 48 if st is None else max(16, st["pool"].shape[0])
+        pool = torch.empty((rows, B), dtype=torch.float32, device=device).bernoulli_(keep).div_(keep)
+        st = _DP_POOL[key] = {"pool": pool, "i": 0, "cap": capturing}
+    r = st["pool"][st["i"]]
+    st["i"] += 1
+    return r
 
 
 class MLP(nn.Module):
@@ -188,6 +206,7 @@ class InherentConsistent(nn.Module):
                 qc = self.query_convs[i]
                 next_Q = Fn.linear(q, qc.weight[:, :, 0], qc.bias)
                 updated_Qs.append(Fn.batch_mean(q))
+        Fn.flush_batch_counters()   # num_batches_tracked of the BatchNorms above: one multi-tensor add
         return feat_maps, updated_Qs
 
 

@@ -95,6 +95,7 @@ class InherentConsistent(nn.Module):
                 qc = self.query_convs[i]
                 next_Q = Fn.linear(q, qc.weight[:, :, 0], qc.bias)
                 updated_Qs.append(Fn.batch_mean(q))
+        Fn.flush_batch_counters()   # num_batches_tracked of the BatchNorms above: one multi-tensor add
         return feat_maps, updated_Qs
 
 

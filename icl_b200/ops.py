@@ -30,6 +30,33 @@ def reduce_ws(device):
     return torch.empty((_lib.lib().icl_reduce_workspace_bytes(),), dtype=torch.uint8, device=device)
 
 
+# Small zero-initialised buffers (statistics, atomics targets, bias gradients: ~200 per training step) are carved from a shared
+# zeroed chunk instead of one fill kernel each.  A region is handed out once and never again; a full chunk is replaced by a fresh
+# torch.zeros (freed when its last slice dies).  A chunk never spans a CUDA-graph capture boundary: the fill must be a node of the
+# graph that uses it, so that every replay starts from zeros.
+_ARENA = {}
+_ARENA_BYTES = 2 << 20
+
+
+def zeros(shape, dtype, device):
+    n = 1
+    for d in shape:
+        n *= int(d)
+    nbytes = ((n * torch.empty((), dtype=dtype).element_size() + 255) // 256) * 256
+    device = torch.device(device)
+    if device.type != "cuda" or nbytes > _ARENA_BYTES // 8 or os.environ.get("ICL_DISABLE_ZERO_ARENA") == "1":
+        return torch.zeros(shape, dtype=dtype, device=device)
+    capturing = torch.cuda.is_current_stream_capturing()
+    key = (device.index if device.index is not None else torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream)
+    a = _ARENA.get(key)
+    if a is None or a[1] + nbytes > _ARENA_BYTES or a[2] != capturing:
+        a = [torch.zeros((_ARENA_BYTES,), dtype=torch.uint8, device=device), 0, capturing]
+        _ARENA[key] = a
+    off = a[1]
+    a[1] += nbytes
+    return a[0][off:off + n * torch.empty((), dtype=dtype).element_size()].view(dtype).view(tuple(shape))
+
+
 def to_ndhwc(x):
     """[B,C,D,H,W] (any strides) -> contiguous [B,D,H,W,C] float32 (no copy if already channels-last)."""
     _require_cuda(x)
@@ -163,7 +190,7 @@ def conv3d_stem_fwd(x, w, bias, B, D, H, W, stats=None):
 
 
 def conv3d_stem_wgrad(x, dy, B, D, H, W):
-    dw = torch.zeros((16, 1, 3, 3, 3), dtype=torch.float32, device=x.device)
+    dw = zeros((16, 1, 3, 3, 3), torch.float32, x.device)
     call("icl_conv3d_stem_wgrad", P(x), P(dy), P(dw), c_int(B), c_int(D), c_int(H), c_int(W), c_int(16),
          gflop=2e-9 * 27 * 16 * B * D * H * W, mbytes=1e-6 * B * D * H * W * 68)
     return dw
@@ -172,8 +199,8 @@ def conv3d_stem_wgrad(x, dy, B, D, H, W):
 def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     """Returns (dw [Cout, sum(cins), 3,3,3], dbias [Cout] or None)."""
     cin_total = sum(cins)
-    dw = torch.zeros((cout, cin_total, 3, 3, 3), dtype=torch.float32, device=dy.device)
-    db = torch.zeros((cout,), dtype=torch.float32, device=dy.device) if want_bias else None
+    dw = zeros((cout, cin_total, 3, 3, 3), torch.float32, dy.device)
+    db = zeros((cout,), torch.float32, dy.device) if want_bias else None
     off = 0
     for i, (x, c) in enumerate(zip(xs, cins)):
         call("icl_conv3d_wgrad", P(x), c_int(c), P(dy), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(db if i == 0 else None),
@@ -229,10 +256,10 @@ def instnorm_relu_fwd(y, mr, want_pk):
 def instnorm_relu_bwd(dA, y, mr, want_pk, want_dbias=False, want_f32=True):
     """Returns (dY or None, dY_pk or None[, dbias]) — dbias = sum of dY over samples and voxels (the conv-bias gradient)."""
     B, D, H, W, C = y.shape
-    red = torch.zeros((B, C, 2), dtype=torch.float64, device=y.device)
+    red = zeros((B, C, 2), torch.float64, y.device)
     dY = torch.empty_like(y) if want_f32 else None
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
-    db = torch.zeros((C,), dtype=torch.float32, device=y.device) if want_dbias else None
+    db = zeros((C,), torch.float32, y.device) if want_dbias else None
     call("icl_instnorm_relu_bwd", P(dA), P(y), P(mr), P(red), P(dY), P(pk), c_int(1 if planes() == 2 else 0), P(db), c_int(B), c_int(C),
          c_ll(D * H * W), tag="B%d r%d C%d" % (B, D, C), mbytes=1e-6 * y.numel() * (16 + (4 if want_f32 else 0) + (2 * planes() if want_pk else 0)))
     return (dY, pk, db) if want_dbias else (dY, pk)
@@ -338,7 +365,7 @@ def linear_dgrad(dy2d, w):
              gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
         return dx
     if M <= 64 and N >= 1024 and K % 4 == 0:
-        dx = torch.zeros((M, K), dtype=torch.float32, device=dy2d.device)
+        dx = zeros((M, K), torch.float32, dy2d.device)
         call("icl_skinny_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), mbytes=4e-6 * (N * K + M * K + M * N),
              gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
     else:

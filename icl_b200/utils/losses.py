@@ -45,7 +45,7 @@ class _ClassStatsFn(torch.autograd.Function):
                 raise RuntimeError("labels shape %s does not match loss grid %s" % (tuple(labels.shape), (B, Z, Y, X)))
         if tgt is not None:
             tgt = ops.to_ndhwc(tgt.detach() if tgt.dim() == 5 else tgt.detach().unsqueeze(2))
-        sums = torch.zeros((3 * K + 1,), dtype=torch.float64, device=s.device)
+        sums = ops.zeros((3 * K + 1,), torch.float64, s.device)
         out2 = torch.empty((2,), dtype=torch.float32, device=s.device)
         call("icl_class_stats_fwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
              P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(out2))
@@ -171,7 +171,7 @@ class _SoftmaxMseFn(torch.autograd.Function):
         S = a_.numel() // (B * K)
         if K > 16:
             raise RuntimeError("icl_b200 softmax_mse supports up to 16 classes")
-        acc = torch.zeros((1,), dtype=torch.float64, device=a.device)
+        acc = ops.zeros((1,), torch.float64, a.device)
         call("icl_softmax_mse", P(a_), P(b_), c_int(B), c_int(K), c_ll(S), P(acc), P(None), c_f(1.0), P(None))
         out = torch.empty((1,), dtype=torch.float32, device=a.device)
         call("icl_scale_to_float", P(acc), c_d(1.0 / float(B * K * S)), P(out))
