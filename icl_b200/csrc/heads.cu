@@ -483,42 +483,53 @@ ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, con
 // pointwise (1x1x1) weight gradient on planar maps: dw[o][i] = sum_{nb, s} dy[nb,o,s] * x[nb,i,s]; db[o] = sum dy.
 // Block = chunk of positions; the dy / x values of 256 positions are staged in shared memory, then thread (o, i) adds its products
 // (CO * (CI + 1) <= 272 pairs, threads stride over them) -> partial[chunk][CO * (CI + 1)]; reduce_chunks_k finishes.
-#define PW_T 256
+#define PW_MAXPAIRS 1024
 __global__ void __launch_bounds__(256) planar_pw_wgrad_partial_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part,
-                                                                 int NB, int CO, int CI, long long S, int chunks) {
-  extern __shared__ float sm[];  // [CO][PW_T] dy, then [CI][PW_T] x
+                                                                 int NB, int CO, int CI, long long S, int chunks, int T) {
+  extern __shared__ float sm[];  // [CO][T] dy, then [CI][T] x
   float* sdy = sm;
-  float* sx = sm + CO * PW_T;
+  float* sx = sm + CO * T;
   const int chunk = blockIdx.x;
   const long long n = (long long)NB * S;
   const long long i0 = n * chunk / chunks, i1 = n * (chunk + 1) / chunks;
   const int pairs = CO * (CI + 1);
-  float acc0 = 0.f, acc1 = 0.f;   // pairs threadIdx.x and threadIdx.x + 256
-  for (long long t0 = i0; t0 < i1; t0 += PW_T) {
-    const long long p = t0 + threadIdx.x;
-    const bool ok = p < i1;
-    const long long nb = ok ? p / S : 0, sp = ok ? p - nb * S : 0;
-    for (int o = 0; o < CO; ++o) sdy[o * PW_T + threadIdx.x] = ok ? dy[(nb * CO + o) * S + sp] : 0.f;
-    for (int i = 0; i < CI; ++i) sx[i * PW_T + threadIdx.x] = ok ? x[(nb * CI + i) * S + sp] : 0.f;
+  float acc[PW_MAXPAIRS / 256];   // pairs threadIdx.x + 256 * k
+#pragma unroll
+  for (int k = 0; k < PW_MAXPAIRS / 256; ++k) acc[k] = 0.f;
+  for (long long t0 = i0; t0 < i1; t0 += T) {
+    for (int j = threadIdx.x; j < T; j += 256) {
+      const long long p = t0 + j;
+      const bool ok = p < i1;
+      const long long nb = ok ? p / S : 0, sp = ok ? p - nb * S : 0;
+      for (int o = 0; o < CO; ++o) sdy[o * T + j] = ok ? dy[(nb * CO + o) * S + sp] : 0.f;
+      for (int i = 0; i < CI; ++i) sx[i * T + j] = ok ? x[(nb * CI + i) * S + sp] : 0.f;
+    }
     __syncthreads();
-    for (int pr = threadIdx.x, k = 0; pr < pairs; pr += 256, ++k) {
-      const int o = pr / (CI + 1), i = pr % (CI + 1);
-      const float* a = sdy + o * PW_T;
-      float s = 0.f;
-      if (i < CI) {
-        const float* b = sx + i * PW_T;
+#pragma unroll
+    for (int k = 0; k < PW_MAXPAIRS / 256; ++k) {
+      const int pr = threadIdx.x + 256 * k;
+      if (pr < pairs) {
+        const int o = pr / (CI + 1), i = pr % (CI + 1);
+        const float* a = sdy + o * T;
+        float s = 0.f;
+        if (i < CI) {
+          const float* b = sx + i * T;
 #pragma unroll 8
-        for (int t = 0; t < PW_T; ++t) s = fmaf(a[t], b[t], s);
-      } else {
+          for (int t = 0; t < T; ++t) s = fmaf(a[t], b[t], s);
+        } else {
 #pragma unroll 8
-        for (int t = 0; t < PW_T; ++t) s += a[t];
+          for (int t = 0; t < T; ++t) s += a[t];
+        }
+        acc[k] += s;
       }
-      if (k == 0) acc0 += s; else acc1 += s;
     }
     __syncthreads();
   }
-  if (threadIdx.x < pairs) part[(long long)chunk * pairs + threadIdx.x] = acc0;
-  if (threadIdx.x + 256 < pairs) part[(long long)chunk * pairs + threadIdx.x + 256] = acc1;
+#pragma unroll
+  for (int k = 0; k < PW_MAXPAIRS / 256; ++k) {
+    const int pr = threadIdx.x + 256 * k;
+    if (pr < pairs) part[(long long)chunk * pairs + pr] = acc[k];
+  }
 }
 __global__ void planar_pw_finalize_k(const float* __restrict__ part, int chunks, int CO, int CI, float* __restrict__ dw, float* __restrict__ db) {
   const int pr = blockIdx.x * blockDim.x + threadIdx.x, pairs = CO * (CI + 1);
@@ -531,10 +542,13 @@ __global__ void planar_pw_finalize_k(const float* __restrict__ part, int chunks,
 }
 ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, float* db, int NB, int CO, int CI, long long S, float* ws, void* stream) {
   ICL_REQUIRE(ws != nullptr, "planar_pw_wgrad: workspace of icl_reduce_workspace_bytes() bytes required");
-  ICL_REQUIRE(CO >= 1 && CI >= 1 && CO * (CI + 1) <= 512 && (CO + CI) * PW_T * 4 <= 48 * 1024, "planar_pw_wgrad: CO=%d CI=%d not supported", CO, CI);
-  const int chunks = red_chunks((long long)NB * S, 4 * PW_T);
-  ICL_REQUIRE((long long)chunks * CO * (CI + 1) * 4 <= RED_WS_BYTES, "planar_pw_wgrad: workspace too small");
-  planar_pw_wgrad_partial_k<<<chunks, 256, (size_t)(CO + CI) * PW_T * 4, as_stream(stream)>>>(dy, x, ws, NB, CO, CI, S, chunks);
+  ICL_REQUIRE(CO >= 1 && CI >= 1 && CO * (CI + 1) <= PW_MAXPAIRS, "planar_pw_wgrad: CO=%d CI=%d not supported (CO * (CI + 1) <= %d)", CO, CI, PW_MAXPAIRS);
+  int T = 256;
+  while (T > 32 && (size_t)(CO + CI) * T * 4 > 40 * 1024) T >>= 1;
+  ICL_REQUIRE((size_t)(CO + CI) * T * 4 <= 48 * 1024, "planar_pw_wgrad: CO=%d CI=%d not supported (shared-memory staging)", CO, CI);
+  int chunks = red_chunks((long long)NB * S, 4 * T);
+  while (chunks > 1 && (long long)chunks * CO * (CI + 1) * 4 > RED_WS_BYTES) chunks >>= 1;
+  planar_pw_wgrad_partial_k<<<chunks, 256, (size_t)(CO + CI) * T * 4, as_stream(stream)>>>(dy, x, ws, NB, CO, CI, S, chunks, T);
   icl_count_launch(1);
   planar_pw_finalize_k<<<cdiv(CO * (CI + 1), 128), 128, 0, as_stream(stream)>>>(ws, chunks, CO, CI, dw, db);
   ICL_LAUNCHED("planar_pw_wgrad");

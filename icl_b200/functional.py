@@ -285,10 +285,17 @@ class BnReluFn(torch.autograd.Function):
 
 
 _PENDING_NBT = []
+_DEFER_NBT = [False]
+
+
+def defer_batch_counters():
+    """From here to flush_batch_counters(), `num_batches_tracked += 1` of the BatchNorms that run is collected instead of launched."""
+    _DEFER_NBT[0] = True
 
 
 def flush_batch_counters():
-    """num_batches_tracked += 1 of every BatchNorm that ran since the last flush, as ONE multi-tensor add (18 per training step)."""
+    """The collected counter increments as ONE multi-tensor add (the ICL heads run 18 BatchNorms per training step)."""
+    _DEFER_NBT[0] = False
     if _PENDING_NBT:
         torch._foreach_add_(list(_PENDING_NBT), 1)
         del _PENDING_NBT[:]
@@ -296,7 +303,10 @@ def flush_batch_counters():
 
 def bn_relu(x, bn, training):
     if training and bn.num_batches_tracked is not None:
-        _PENDING_NBT.append(bn.num_batches_tracked)
+        if _DEFER_NBT[0]:
+            _PENDING_NBT.append(bn.num_batches_tracked)
+        else:
+            bn.num_batches_tracked += 1
     return BnReluFn.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, training, bn.momentum, bn.eps)
 
 

@@ -75,6 +75,7 @@ class InherentConsistent(nn.Module):
         BS = feats[0].shape[0]
         if modal not in ("labeled", "unlabeled"):
             return feat_maps, updated_Qs
+        Fn.defer_batch_counters()
         labeled = modal == "labeled"
         need_q = need_queries or labeled
         next_Q = self.guided_Q.expand(BS, -1, -1) if labeled else None
