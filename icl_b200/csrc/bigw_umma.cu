@@ -341,35 +341,49 @@ ICL_API int icl_bigw_linear_dgrad(int rows, int N, int K, const float* dy, const
 // =====================================================================================================================
 #define SF_MT 128
 #define SF_NT 256
-#define SF_RC 32                                   // factor rows per pipeline stage
-#define SF_A_PLANE (SF_MT / 8 * SF_RC * 16)        // 8 KB
-#define SF_B_PLANE (SF_NT / 8 * SF_RC * 16)        // 16 KB
-#define SF_STAGE (2 * SF_A_PLANE + 2 * SF_B_PLANE) // 48 KB
-#define SF_STAGES 2
+#define SF_RC 16                                   // factor rows per pipeline stage (one K = 16 MMA step)
+#define SF_A_PLANE (SF_MT / 8 * SF_RC * 16)        // 4 KB
+#define SF_B_PLANE (SF_NT / 8 * SF_RC * 16)        // 8 KB
+#define SF_STAGE (2 * SF_A_PLANE + 2 * SF_B_PLANE) // 24 KB
+#define SF_MAX_STAGES 6
 #define SF_SL 32                                   // weight columns per p/m slice
 #define SF_PM_TILE (SF_MT * SF_SL * 4)             // 16 KB
-#define SF_PM_STAGES 4
+#define SF_MAX_PM_STAGES 4
+#define SF_BAND 8                                  // o-tiles per rasterisation band (tile order: see sf_tile)
 
 struct SgdFacParams {
   int tiles_n, tiles_k, num_tiles, rchunks;
+  int op_stages, pm_stages;   // pipeline depths: factor stages (24 KB each) and p/m slice stages (32 KB each)
   int a_groups, b_groups;  // N/8 and K/8 (outer extent of one precision plane in the factor maps)
   float mu, wd;
   const float* lr;
 };
 
+// Tile order.  A wave of 148 consecutive tiles covers SF_BAND weight-row tiles x ~18 weight-column tiles, so the factor slabs it
+// reads (8 x A + 18 x B) are shared through L2 by the whole wave instead of every CTA of a wave reading a different B slab
+// (at R = 1024 the packed factors are 113 MB: row-major order re-reads them from HBM, 8.9 GB per weight).
+__device__ __forceinline__ void sf_tile(int t, const SgdFacParams& p, int& tn, int& tk) {
+  const int per_band = SF_BAND * p.tiles_k;
+  const int band = t / per_band, local = t - band * per_band;
+  const int rows = min(SF_BAND, p.tiles_n - band * SF_BAND);
+  tk = local / rows;
+  tn = band * SF_BAND + (local - tk * rows);
+}
+
 __global__ void __launch_bounds__(224, 1)
 sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ CUtensorMap mapP,
                     const __grid_constant__ CUtensorMap mapM, const SgdFacParams p) {
   extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t bars[2 * SF_STAGES + 2 * SF_PM_STAGES + 4];
+  __shared__ __align__(8) uint64_t bars[2 * SF_MAX_STAGES + 2 * SF_MAX_PM_STAGES + 4];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem0 = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int SF_STAGES = p.op_stages, SF_PM_STAGES = p.pm_stages;
   const uint32_t pm0 = smem0;                                       // p/m stages first (1024-byte aligned swizzled tiles)
   const uint32_t op0 = smem0 + SF_PM_STAGES * 2 * SF_PM_TILE;
-  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SF_STAGES]);
-  const uint32_t pmfull0 = smem_u32(&bars[2 * SF_STAGES]), pmempty0 = smem_u32(&bars[2 * SF_STAGES + SF_PM_STAGES]);
-  const uint32_t accfull0 = smem_u32(&bars[2 * SF_STAGES + 2 * SF_PM_STAGES]), accempty0 = accfull0 + 16;
+  const uint32_t full0 = smem_u32(&bars[0]), empty0 = smem_u32(&bars[SF_MAX_STAGES]);
+  const uint32_t pmfull0 = smem_u32(&bars[2 * SF_MAX_STAGES]), pmempty0 = smem_u32(&bars[2 * SF_MAX_STAGES + SF_MAX_PM_STAGES]);
+  const uint32_t accfull0 = smem_u32(&bars[2 * SF_MAX_STAGES + 2 * SF_MAX_PM_STAGES]), accempty0 = accfull0 + 16;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < SF_STAGES; ++s) { mbar_init(full0 + 8 * s, 1); mbar_init(empty0 + 8 * s, 1); }
@@ -394,7 +408,8 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ================================ factor producer ================================
     int stage = 0; uint32_t phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int tn = t / p.tiles_k, tk = t % p.tiles_k;
+      int tn, tk;
+      sf_tile(t, p, tn, tk);
       for (int rc = 0; rc < p.rchunks; ++rc) {
         mbar_wait(empty0 + 8 * stage, phase ^ 1, 100 + stage);
         const uint32_t sa = op0 + stage * SF_STAGE, fb = full0 + 8 * stage;
@@ -449,7 +464,8 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
     // ================================ p / m tile producer ================================
     int ps = 0; uint32_t pphase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int tn = t / p.tiles_k, tk = t % p.tiles_k;
+      int tn, tk;
+      sf_tile(t, p, tn, tk);
       for (int sl = 0; sl < SF_NT / SF_SL; ++sl) {
         mbar_wait(pmempty0 + 8 * ps, pphase ^ 1, 600 + ps);
         const uint32_t sp_ = pm0 + ps * 2 * SF_PM_TILE, fb = pmfull0 + 8 * ps;
@@ -469,9 +485,9 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const float lr = *p.lr, mu = p.mu, wd = p.wd;
     int ps = 0; uint32_t pphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    int prev_ps = -1;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const int tn = t / p.tiles_k, tk = t % p.tiles_k;
+      int tn, tk;
+      sf_tile(t, p, tn, tk);
       mbar_wait(accfull0 + 8 * acc, acc_phase, 400 + acc);
       tc_fence_after();
       for (int sl = 0; sl < SF_NT / SF_SL; ++sl) {
@@ -500,10 +516,11 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
           tma_store_2d(&mapP, tp, tk * SF_NT + sl * SF_SL, tn * SF_MT);
           tma_store_2d(&mapM, tp + SF_PM_TILE, tk * SF_NT + sl * SF_SL, tn * SF_MT);
           bulk_commit();
-          // the previous slice's stores have finished READING shared memory once at most one group is pending
-          if (prev_ps >= 0) { bulk_wait_read<1>(); mbar_arrive(pmempty0 + 8 * prev_ps); }
+          // the stage can be refilled as soon as the stores have finished READING it (a few hundred cycles; the other 127 threads
+          // are already on the next slice)
+          bulk_wait_read<0>();
+          mbar_arrive(pmempty0 + 8 * ps);
         }
-        prev_ps = ps;
         if (++ps == SF_PM_STAGES) { ps = 0; pphase ^= 1; }
       }
       tc_fence_before();
@@ -584,10 +601,15 @@ ICL_API int icl_sgd_factored_apply(int R_total, int N, int K, const void* worksp
   SgdFacParams q;
   q.tiles_n = cdiv(N, SF_MT); q.tiles_k = cdiv(K, SF_NT); q.num_tiles = q.tiles_n * q.tiles_k; q.rchunks = Rpad / SF_RC;
   q.a_groups = N / 8; q.b_groups = K / 8; q.mu = mu; q.wd = wd; q.lr = lr_ptr;
-  const size_t smem = SF_PM_STAGES * 2 * SF_PM_TILE + SF_STAGES * SF_STAGE + 1024;
+  // few factor rows: the p / m stream is everything (deep p/m pipeline); many rows: the MMAs and their operand loads dominate and the
+  // epilogue hides behind them through the double-buffered accumulator (deep factor pipeline)
+  if (q.rchunks <= 8) { q.pm_stages = 4; q.op_stages = 3; }
+  else if (q.rchunks <= 32) { q.pm_stages = 3; q.op_stages = 4; }
+  else { q.pm_stages = 2; q.op_stages = SF_MAX_STAGES; }
+  const size_t smem = (size_t)q.pm_stages * 2 * SF_PM_TILE + (size_t)q.op_stages * SF_STAGE + 1024;
   static bool configured = false;
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(sgd_factored_umma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(sgd_factored_umma_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(226 * 1024));
     if (e != cudaSuccess) { icl_set_error("sgd_factored_apply: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
     configured = true;
   }
