@@ -354,6 +354,7 @@ ICL_API int icl_bigw_linear_dgrad(int rows, int N, int K, const float* dy, const
 struct SgdFacParams {
   int tiles_n, tiles_k, num_tiles, rchunks;
   int op_stages, pm_stages;   // pipeline depths: factor stages (24 KB each) and p/m slice stages (32 KB each)
+  int band;                   // weight-row tiles per rasterisation band (1 = row-major tile order)
   int a_groups, b_groups;  // N/8 and K/8 (outer extent of one precision plane in the factor maps)
   float mu, wd;
   const float* lr;
@@ -363,11 +364,11 @@ struct SgdFacParams {
 // reads (8 x A + 18 x B) are shared through L2 by the whole wave instead of every CTA of a wave reading a different B slab
 // (at R = 1024 the packed factors are 113 MB: row-major order re-reads them from HBM, 8.9 GB per weight).
 __device__ __forceinline__ void sf_tile(int t, const SgdFacParams& p, int& tn, int& tk) {
-  const int per_band = SF_BAND * p.tiles_k;
+  const int per_band = p.band * p.tiles_k;
   const int band = t / per_band, local = t - band * per_band;
-  const int rows = min(SF_BAND, p.tiles_n - band * SF_BAND);
+  const int rows = min(p.band, p.tiles_n - band * p.band);
   tk = local / rows;
-  tn = band * SF_BAND + (local - tk * rows);
+  tn = band * p.band + (local - tk * rows);
 }
 
 __global__ void __launch_bounds__(224, 1)
@@ -485,6 +486,7 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const float lr = *p.lr, mu = p.mu, wd = p.wd;
     int ps = 0; uint32_t pphase = 0;
     int acc = 0; uint32_t acc_phase = 0;
+    int prev_ps = -1;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       int tn, tk;
       sf_tile(t, p, tn, tk);
@@ -516,11 +518,18 @@ sgd_factored_umma_k(const __grid_constant__ CUtensorMap mapA, const __grid_const
           tma_store_2d(&mapP, tp, tk * SF_NT + sl * SF_SL, tn * SF_MT);
           tma_store_2d(&mapM, tp + SF_PM_TILE, tk * SF_NT + sl * SF_SL, tn * SF_MT);
           bulk_commit();
-          // the stage can be refilled as soon as the stores have finished READING it (a few hundred cycles; the other 127 threads
-          // are already on the next slice)
-          bulk_wait_read<0>();
-          mbar_arrive(pmempty0 + 8 * ps);
+          if (SF_PM_STAGES <= 2) {
+            // shallow p/m pipeline (large R): refill the stage as soon as the stores have finished READING it (a few hundred
+            // cycles; the other 127 threads are already on the next slice)
+            bulk_wait_read<0>();
+            mbar_arrive(pmempty0 + 8 * ps);
+          } else if (prev_ps >= 0) {
+            // the previous slice's stores have finished reading shared memory once at most one group is pending
+            bulk_wait_read<1>();
+            mbar_arrive(pmempty0 + 8 * prev_ps);
+          }
         }
+        prev_ps = ps;
         if (++ps == SF_PM_STAGES) { ps = 0; pphase ^= 1; }
       }
       tc_fence_before();
@@ -603,9 +612,9 @@ ICL_API int icl_sgd_factored_apply(int R_total, int N, int K, const void* worksp
   q.a_groups = N / 8; q.b_groups = K / 8; q.mu = mu; q.wd = wd; q.lr = lr_ptr;
   // few factor rows: the p / m stream is everything (deep p/m pipeline); many rows: the MMAs and their operand loads dominate and the
   // epilogue hides behind them through the double-buffered accumulator (deep factor pipeline)
-  if (q.rchunks <= 8) { q.pm_stages = 4; q.op_stages = 3; }
-  else if (q.rchunks <= 32) { q.pm_stages = 3; q.op_stages = 4; }
-  else { q.pm_stages = 2; q.op_stages = SF_MAX_STAGES; }
+  if (q.rchunks <= 8) { q.pm_stages = 4; q.op_stages = 3; q.band = 1; }
+  else if (q.rchunks <= 24) { q.pm_stages = 3; q.op_stages = 4; q.band = 1; }
+  else { q.pm_stages = 2; q.op_stages = SF_MAX_STAGES; q.band = SF_BAND; }
   const size_t smem = (size_t)q.pm_stages * 2 * SF_PM_TILE + (size_t)q.op_stages * SF_STAGE + 1024;
   static bool configured = false;
   if (!configured) {

@@ -75,6 +75,24 @@ def sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_class
     return score, cnt, pads
 
 
+_PINNED = {}
+
+
+def _label_to_host(label):
+    """Device int64 label map -> numpy int64.  Class ids fit one byte, so 1 byte per voxel crosses PCIe (through a cached pinned
+    buffer) instead of 8, and the widening back to the reference's int64 happens on the host."""
+    small = label.to(torch.uint8)
+    key = (small.numel(), label.device.index)
+    buf = _PINNED.get(key)
+    if buf is None:
+        if len(_PINNED) > 4:
+            _PINNED.clear()
+        buf = _PINNED[key] = torch.empty((small.numel(),), dtype=torch.uint8).pin_memory()
+    buf.copy_(small.reshape(-1), non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return buf.numpy().reshape(tuple(label.shape)).astype(np.int64)
+
+
 def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1, inference_kw=False, window_batch=1):
     """numpy [w,h,d] in -> numpy int64 label map out (host-blocking, like the reference)."""
     w, h, d = image.shape
@@ -82,7 +100,7 @@ def test_single_case(net, image, stride_xy, stride_z, patch_size, num_classes=1,
                                              window_batch=window_batch)
     label = _finalize(score, cnt)
     label = label[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
-    return label.cpu().numpy()
+    return _label_to_host(label)
 
 
 test_single_case.__test__ = False  # not a pytest test
@@ -105,7 +123,7 @@ def test_single_case_sharded(net, image, stride_xy, stride_z, patch_size, num_cl
         dist.all_reduce(cnt, group=group)
     label = _finalize(score, cnt)
     label = label[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
-    return label.cpu().numpy()
+    return _label_to_host(label)
 
 
 test_single_case_sharded.__test__ = False  # not a pytest test
@@ -128,3 +146,39 @@ def dice_metric(pred, gt):
     else:
         dice = 0.0
     return dice, (inter, na, nb)
+
+
+def cal_metric_dice(gt, pred):
+    """Dice half of cal_metric (val_3D.py:85-97) for one class: binarise, exact integer counts on the device, the reference's
+    empty-set conventions (both empty -> 1, one empty -> 0).  HD95 is out of scope (MedPy / scipy CPU code)."""
+    return dice_metric(pred, gt)[0]
+
+
+def test_all_case(net, cases, num_classes=2, patch_size=(96, 96, 96), stride_xy=64, stride_z=64, window_batch=4, inference_kw=False,
+                  group=None):
+    """In-training validation driver — test_all_case_base (val_3D.py:100-118; called every 200 iterations by
+    train_inherent_consistent_unet_3D_BraTS.py:135-137) on in-memory cases instead of an h5 list: `cases` yields (image [w,h,d],
+    label [w,h,d]) arrays or tensors.  Every case runs the device-resident sliding window (windows batched, sharded over the ranks
+    of an initialised process group), argmax and the per-class Dice counts stay on the GPU; nothing but one float per (case, class)
+    crosses PCIe.  Returns metric_cal like the reference: a list over classes 1..num_classes-1 of per-case (dice, hd95) tuples, with
+    hd95 = nan (out of scope)."""
+    import torch.distributed as dist
+    on = dist.is_available() and dist.is_initialized()
+    rank, world = (dist.get_rank(group), dist.get_world_size(group)) if on else (0, 1)
+    dev = next(net.parameters()).device
+    metric_cal = [[] for _ in range(num_classes - 1)]
+    for image, label in cases:
+        w, h, d = image.shape
+        score, cnt, pads = sliding_window_scores(net, image, stride_xy, stride_z, patch_size, num_classes, rank=rank, world_size=world,
+                                                 inference_kw=inference_kw, window_batch=window_batch)
+        if world > 1:
+            dist.all_reduce(score, group=group)
+            dist.all_reduce(cnt, group=group)
+        pred = _finalize(score, cnt)[pads[0][0]:pads[0][0] + w, pads[1][0]:pads[1][0] + h, pads[2][0]:pads[2][0] + d]
+        gt = (label if isinstance(label, torch.Tensor) else torch.as_tensor(np.asarray(label))).to(dev).long()
+        for i in range(1, num_classes):
+            metric_cal[i - 1].append((cal_metric_dice((gt == i).long(), (pred == i).long()), float("nan")))
+    return metric_cal
+
+
+test_all_case.__test__ = False  # not a pytest test

@@ -230,3 +230,27 @@ def test_sliding_window_config5_grid(stride, window_batch):
         # window batching must not change the result beyond fp32 re-association of nothing: the accumulation order is the same
         again = inference.test_single_case(net, image, stride, stride, patch, num_classes=K, window_batch=4)
         assert float((again == label).mean()) >= 0.99999
+
+
+def test_validation_driver_matches_oracle():
+    """inference.test_all_case (in-training validation, val_3D.py:100-118): per-case per-class Dice equals the oracle's
+    restatement (CPU sliding window + MedPy-dc restatement) on the same label maps; counts bit-exact on identical maps."""
+    from icl_b200 import inference
+    from icl_b200.networks.unet_3D import unet_3D
+    K, patch = 2, (96, 96, 96)
+    net = unet_3D(feature_scale=4, n_classes=K, in_channels=1)
+    synth.load_synth(net, 77)
+    net.cuda().eval()
+    cases = [(synth.synth_volume((112, 96, 100), 90 + i).numpy(), synth.synth_blobs((112, 96, 100), K, 95 + i).numpy()) for i in range(2)]
+    got = inference.test_all_case(net, cases, num_classes=K, patch_size=patch, stride_xy=64, stride_z=64, window_batch=2)
+    assert len(got) == K - 1 and len(got[0]) == len(cases)
+    P = R.make_params({k: v.detach().cpu() for k, v in net.state_dict().items()}, requires_grad=False)
+    for ci, (image, label) in enumerate(cases):
+        with torch.no_grad():
+            want = R.test_single_case(lambda p: R.unet_3d_forward(P, p), image, 64, 64, patch, K)
+        pred = inference.test_single_case(net, image, 64, 64, patch, num_classes=K, window_batch=2)
+        assert float((pred == want).mean()) >= 0.999
+        d_ref, counts_ref = R.dice_metric((pred == 1), (label == 1))           # on OUR label map: counts must be bit-exact
+        d_mine, counts = inference.dice_metric(torch.from_numpy((pred == 1).astype(np.int64)).cuda(), torch.from_numpy((label == 1).astype(np.int64)).cuda())
+        assert tuple(counts) == tuple(counts_ref) and d_mine == d_ref
+        assert abs(got[0][ci][0] - d_ref) < 1e-12
