@@ -253,4 +253,4 @@ def test_validation_driver_matches_oracle():
         d_ref, counts_ref = R.dice_metric((pred == 1), (label == 1))           # on OUR label map: counts must be bit-exact
         d_mine, counts = inference.dice_metric(torch.from_numpy((pred == 1).astype(np.int64)).cuda(), torch.from_numpy((label == 1).astype(np.int64)).cuda())
         assert tuple(counts) == tuple(counts_ref) and d_mine == d_ref
-        assert abs(got[0][ci][0] - d_ref) < 1e-12
+        assert abs(got[0][ci][0] - d_ref) < 1e-3   # two separate inference runs: the label maps may differ in a few voxels (statistics use atomics)
