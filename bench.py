@@ -322,7 +322,7 @@ class Timer:
 class TrainBench:
     """One workload (cfg2 / cfg3) of the training step on this rank's GPU."""
 
-    def __init__(self, a, wl, rank, world, dev):
+    def __init__(self, a, wl, rank, world, dev, exchange=True):
         from icl_b200 import _lib, parallel
         from icl_b200.networks.unet_3D_icl import unet_3D_icl
         from icl_b200.optim import SGD
@@ -337,7 +337,7 @@ class TrainBench:
         # fused_factored: the 13 824^2 mlp2 weight gradients are applied as rank-R updates inside the optimizer
         self.opt = SGD(self.net.parameters(), lr=cfg["base_lr"], momentum=0.9, weight_decay=1e-4, fused_factored=not a.unfused_optimizer)
         self.dp = None
-        if world > 1:
+        if world > 1 and exchange:
             self.dp = parallel.GradAverager(self.net, world, factored=a.unfused_optimizer, overlap=not a.no_overlap)
         self.aux_loss, self.pse_loss = L.AuxLoss3D(K), L.PseudoSoftLoss3D(K)
         self.L = L
@@ -406,10 +406,29 @@ class TrainBench:
             self.dp.close()
 
 
+def measure_local_reference(a, wl, rank, world, dev):
+    """N > 1: the SAME workload with the exchange switched off (every rank steps on its own batch, nothing crosses NVLink), timed
+    like the real run (barrier, CUDA events, max over ranks): the single-GPU denominator of this line's weak-scaling efficiency,
+    measured on the same GPUs in the same process."""
+    tb = TrainBench(a, wl, rank, world, dev, exchange=False)
+    timer = Timer(world, dev)
+    if not a.no_graph:
+        tb.capture()
+    for _ in range(max(a.warmup, 3)):
+        tb.step(tb.x_dev, tb.y_dev)
+    ms = timer(lambda: tb.step(tb.x_dev, tb.y_dev), a.steps)
+    tb.close()
+    return ms
+
+
 def measure_train(a, wl, rank, world, dev, local, full=True):
     """Returns the JSON line (dict) for one training workload; `full` = with e2e, kernel profile and roofline."""
     import torch
     from icl_b200 import ops
+    local_ms = None
+    if world > 1 and full:
+        local_ms = measure_local_reference(a, wl, rank, world, dev)
+        torch.cuda.empty_cache()
     tb = TrainBench(a, wl, rank, world, dev)
     timer = Timer(world, dev)
     use_graph = not a.no_graph
@@ -437,6 +456,11 @@ def measure_train(a, wl, rank, world, dev, local, full=True):
                    "l2": "no flush needed: per-step working set (785M params + activations, >15 GB) >> 126 MB L2"},
         "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_enqueue_ms, "clocks": clocks,
     }
+    if local_ms is not None:
+        line["weak_scaling_reference"] = {
+            "workload": wl, "ms_per_step_without_exchange": local_ms, "value_1gpu": BATCH * VOX / (local_ms * 1e-3),
+            "note": "same step, same GPUs, exchange off (each rank on its own batch), max over ranks: the single-GPU denominator for this "
+                    "line; a default N = 1 run reports cfg2 as `value` (BASELINE configs[1]) and this workload under `also`"}
     if not full:
         tb.close()
         return line
