@@ -31,8 +31,12 @@ def main():
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = json.load(open(pk)).get("hbm_gbs", 6546.2) if os.path.exists(pk) else 6546.2
     only = sys.argv[1] if len(sys.argv) > 1 else ""
+    rows_only = int(sys.argv[2]) if len(sys.argv) > 2 else 0      # restrict to one row count (ncu captures)
+    r_only = int(sys.argv[3]) if len(sys.argv) > 3 else 0         # restrict the sgd sweep to one R
     g = torch.Generator(device="cuda").manual_seed(1)
     for rows, n in ((16, 13824), (128, 13824), (32, 1728), (256, 1728)):
+        if rows_only and rows != rows_only:
+            continue
         x = torch.randn(rows, n, device="cuda", generator=g)
         w = torch.randn(n, n, device="cuda", generator=g) * 0.01
         b = torch.zeros(n, device="cuda")
@@ -51,6 +55,8 @@ def main():
             m = torch.zeros_like(w)
             lr = torch.full((1,), 0.01, device="cuda")
             for R in (32, 64, 256, 512, 1024, 2048):
+                if r_only and R != r_only:
+                    continue
                 dy = torch.randn(R, n, device="cuda", generator=g) * 0.01
                 xx = torch.randn(R, n, device="cuda", generator=g)
                 for mode in ("umma", "legacy"):
