@@ -486,9 +486,10 @@ ICL_API int icl_bn_relu_bwd(const float* dy, const float* x, const float* y, con
 #define PW_MAXPAIRS 1024
 __global__ void __launch_bounds__(256) planar_pw_wgrad_partial_k(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ part,
                                                                  int NB, int CO, int CI, long long S, int chunks, int T) {
-  extern __shared__ float sm[];  // [CO][T] dy, then [CI][T] x
+  extern __shared__ float sm[];  // [CO][T + 1] dy, then [CI][T + 1] x (odd row stride: the pair threads of a warp read different rows)
+  const int TS = T + 1;
   float* sdy = sm;
-  float* sx = sm + CO * T;
+  float* sx = sm + CO * TS;
   const int chunk = blockIdx.x;
   const long long n = (long long)NB * S;
   const long long i0 = n * chunk / chunks, i1 = n * (chunk + 1) / chunks;
@@ -501,8 +502,8 @@ __global__ void __launch_bounds__(256) planar_pw_wgrad_partial_k(const float* __
       const long long p = t0 + j;
       const bool ok = p < i1;
       const long long nb = ok ? p / S : 0, sp = ok ? p - nb * S : 0;
-      for (int o = 0; o < CO; ++o) sdy[o * T + j] = ok ? dy[(nb * CO + o) * S + sp] : 0.f;
-      for (int i = 0; i < CI; ++i) sx[i * T + j] = ok ? x[(nb * CI + i) * S + sp] : 0.f;
+      for (int o = 0; o < CO; ++o) sdy[o * TS + j] = ok ? dy[(nb * CO + o) * S + sp] : 0.f;
+      for (int i = 0; i < CI; ++i) sx[i * TS + j] = ok ? x[(nb * CI + i) * S + sp] : 0.f;
     }
     __syncthreads();
 #pragma unroll
@@ -510,10 +511,10 @@ __global__ void __launch_bounds__(256) planar_pw_wgrad_partial_k(const float* __
       const int pr = threadIdx.x + 256 * k;
       if (pr < pairs) {
         const int o = pr / (CI + 1), i = pr % (CI + 1);
-        const float* a = sdy + o * T;
+        const float* a = sdy + o * TS;
         float s = 0.f;
         if (i < CI) {
-          const float* b = sx + i * T;
+          const float* b = sx + i * TS;
 #pragma unroll 8
           for (int t = 0; t < T; ++t) s = fmaf(a[t], b[t], s);
         } else {
@@ -544,11 +545,11 @@ ICL_API int icl_planar_pw_wgrad(const float* dy, const float* x, float* dw, floa
   ICL_REQUIRE(ws != nullptr, "planar_pw_wgrad: workspace of icl_reduce_workspace_bytes() bytes required");
   ICL_REQUIRE(CO >= 1 && CI >= 1 && CO * (CI + 1) <= PW_MAXPAIRS, "planar_pw_wgrad: CO=%d CI=%d not supported (CO * (CI + 1) <= %d)", CO, CI, PW_MAXPAIRS);
   int T = 256;
-  while (T > 32 && (size_t)(CO + CI) * T * 4 > 40 * 1024) T >>= 1;
-  ICL_REQUIRE((size_t)(CO + CI) * T * 4 <= 48 * 1024, "planar_pw_wgrad: CO=%d CI=%d not supported (shared-memory staging)", CO, CI);
-  int chunks = red_chunks((long long)NB * S, 4 * T);
+  while (T > 32 && (size_t)(CO + CI) * (T + 1) * 4 > 40 * 1024) T >>= 1;
+  ICL_REQUIRE((size_t)(CO + CI) * (T + 1) * 4 <= 48 * 1024, "planar_pw_wgrad: CO=%d CI=%d not supported (shared-memory staging)", CO, CI);
+  int chunks = red_chunks((long long)NB * S, T);   // one staged tile per block while blocks are scarce
   while (chunks > 1 && (long long)chunks * CO * (CI + 1) * 4 > RED_WS_BYTES) chunks >>= 1;
-  planar_pw_wgrad_partial_k<<<chunks, 256, (size_t)(CO + CI) * T * 4, as_stream(stream)>>>(dy, x, ws, NB, CO, CI, S, chunks, T);
+  planar_pw_wgrad_partial_k<<<chunks, 256, (size_t)(CO + CI) * (T + 1) * 4, as_stream(stream)>>>(dy, x, ws, NB, CO, CI, S, chunks, T);
   icl_count_launch(1);
   planar_pw_finalize_k<<<cdiv(CO * (CI + 1), 128), 128, 0, as_stream(stream)>>>(ws, chunks, CO, CI, dw, db);
   ICL_LAUNCHED("planar_pw_wgrad");

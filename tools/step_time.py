@@ -14,6 +14,9 @@ from icl_b200.utils import losses as L  # noqa: E402
 def run(name, net, x, y, n_lab, size, iters=5):
     K = 4
     net.cuda().train()
+    graph = "--graph" in sys.argv
+    from icl_b200.optim import SGD
+    opt = SGD(net.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4, fused_factored=True) if graph else None
     aux, pse = L.AuxLoss(K, resize=[size, size]), L.PseudoSoftLoss(K, resize=[size, size])
     ce_l, dice_l = L.CrossEntropyLoss(), L.DiceLoss(K)
 
@@ -24,9 +27,21 @@ def run(name, net, x, y, n_lab, size, iters=5):
         loss = ce_l(o[0], y[:n_lab].long()) + dice_l(o[0], y[:n_lab].unsqueeze(1), softmax=True) + aux(o[2], y[:n_lab]) \
             + pse(o[3], o[1]) + 50 * L.softmax_mse_loss(o[3], o[4])
         loss.backward()
+        if opt is not None:
+            opt.step()
         return loss
     for _ in range(2):
         step()
+    if graph:
+        from icl_b200.graph import GraphedStep
+        eager = step
+        try:
+            g = GraphedStep(lambda: eager(), (), opt, warmup=1)
+            step = lambda: g()   # noqa: E731
+            name += " [cuda-graph replay, incl. fused SGD step]"
+        except Exception as e:  # report, then time the eager step
+            print("%s: graph capture failed: %r" % (name, e), flush=True)
+            name += " [eager, incl. fused SGD step]"
     torch.cuda.synchronize()
     ts = []
     for _ in range(iters):
