@@ -79,7 +79,8 @@ class LayerNormFn(torch.autograd.Function):
         rows = x2.shape[0]
         y = torch.empty_like(x2)
         mr = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
-        call("icl_layernorm_fwd", P(x2), P(w.detach()), P(b.detach()), P(y), P(mr), c_ll(rows), c_int(C), c_f(eps))
+        call("icl_layernorm_fwd", P(x2), P(w.detach()), P(b.detach()), P(y), P(mr), c_ll(rows), c_int(C), c_f(eps), mbytes=8e-6 * rows * C,
+             tag="%dx%d" % (rows, C))
         ctx.save_for_backward(x2, w.detach(), mr)
         ctx.xshape = x.shape
         return y.reshape(x.shape)
@@ -93,7 +94,8 @@ class LayerNormFn(torch.autograd.Function):
         want_w = ctx.needs_input_grad[1] or ctx.needs_input_grad[2]
         dw = ops.zeros((C,), torch.float32, g.device) if want_w else None
         db = ops.zeros((C,), torch.float32, g.device) if want_w else None
-        call("icl_layernorm_bwd", P(g), P(x2), P(w), P(mr), P(dx), P(dw), P(db), c_ll(x2.shape[0]), c_int(C))
+        call("icl_layernorm_bwd", P(g), P(x2), P(w), P(mr), P(dx), P(dw), P(db), c_ll(x2.shape[0]), c_int(C), mbytes=12e-6 * x2.numel(),
+             tag="%dx%d" % (x2.shape[0], C))
         return (dx.reshape(ctx.xshape) if dx is not None else None), dw, db, None
 
 
@@ -116,7 +118,8 @@ class ProxyAttnFn(torch.autograd.Function):
         xv = torch.empty((B, K, C), dtype=torch.float32, device=ql.device) if want_xv else None
         mstat = torch.empty((B * H * K, 2), dtype=torch.float32, device=ql.device) if want_xv else None
         call("icl_proxy_attn_fwd", P(ql_), P(kv_), P(amap), P(xv), P(mstat), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K),
-             c_f(scale), c_int(1 if want_xv else 0))
+             c_f(scale), c_int(1 if want_xv else 0), mbytes=4e-6 * (B * N * C * (2 if want_xv else 1) + B * K * H * N),
+             tag="B%d N%d C%d H%d K%d" % (B, N, C, H, K))
         ctx.save_for_backward(ql_, kv_, amap, mstat)
         ctx.dims = (B, N, C, H, K, scale)
         ctx.set_materialize_grads(False)
@@ -132,7 +135,8 @@ class ProxyAttnFn(torch.autograd.Function):
         dql = torch.empty_like(ql_)
         dkv = torch.empty_like(kv_)
         call("icl_proxy_attn_bwd", P(None if dmap is None else _c(dmap)), P(None if dxv is None else _c(dxv)), P(amap), P(ql_), P(kv_),
-             P(mstat), P(dl), P(dql), P(dkv), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K), c_f(scale))
+             P(mstat), P(dl), P(dql), P(dkv), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K), c_f(scale),
+             mbytes=4e-6 * (2 * B * N * 2 * C + 3 * B * K * H * N), tag="B%d N%d C%d H%d K%d" % (B, N, C, H, K))
         return dql, dkv, None, None
 
 

@@ -404,7 +404,7 @@ def outer_wgrad_acc(dy2d, x2d, dW):
 
 def gelu_bwd(dy, pre):
     dx = torch.empty_like(pre)
-    call("icl_gelu_bwd", P(dy), P(pre), P(dx), c_ll(pre.numel()))
+    call("icl_gelu_bwd", P(dy), P(pre), P(dx), c_ll(pre.numel()), mbytes=12e-6 * pre.numel())
     return dx
 
 
@@ -414,7 +414,7 @@ def axpby(x, y, alpha, beta):
 
 def row_combine(a, sa, b, sb, rows):
     out = torch.empty_like(a)
-    call("icl_row_combine", P(a), P(sa), P(b), P(sb), P(out), c_ll(rows), c_ll(a.numel() // rows))
+    call("icl_row_combine", P(a), P(sa), P(b), P(sb), P(out), c_ll(rows), c_ll(a.numel() // rows), mbytes=4e-6 * a.numel() * (3 if b is not None else 2))
     return out
 
 

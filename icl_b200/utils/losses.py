@@ -48,7 +48,8 @@ class _ClassStatsFn(torch.autograd.Function):
         sums = ops.zeros((3 * K + 1,), torch.float64, s.device)
         out2 = torch.empty((2,), dtype=torch.float32, device=s.device)
         call("icl_class_stats_fwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
-             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(out2))
+             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(out2),
+             mbytes=1e-6 * (s.numel() * 4 + B * Z * Y * X * (8 if labels is not None else 4 * K)), tag="K%d r%d->%d %s" % (K, rx, X, "labels" if labels is not None else "soft"))
         ctx.save_for_backward(s, labels, tgt, sums, class_w)
         ctx.meta = (planar, (rz, ry, rx), B, K, (Z, Y, X), is_prob, src.shape)
         ctx.set_materialize_grads(False)
@@ -66,7 +67,8 @@ class _ClassStatsFn(torch.autograd.Function):
         gc = None if g_ce is None else g_ce.detach().float().contiguous()
         gd = None if g_dice is None else g_dice.detach().float().contiguous()
         call("icl_class_stats_bwd", P(s), c_int(planar), c_int(rz), c_int(ry), c_int(rx), c_int(B), c_int(K), c_int(Z), c_int(Y), c_int(X),
-             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(gc), P(gd), c_f(1.0), c_f(1.0), P(ds), P(ws))
+             P(labels), P(tgt), c_int(1 if is_prob else 0), P(class_w), P(sums), P(gc), P(gd), c_f(1.0), c_f(1.0), P(ds), P(ws),
+             mbytes=1e-6 * (2 * s.numel() * 4 + B * Z * Y * X * (8 if labels is not None else 4 * K)), tag="K%d r%d->%d %s" % (K, rx, X, "labels" if labels is not None else "soft"))
         if len(shape) == 4:
             ds = ds.squeeze(2)
         return ds, None, None, None, None, None
