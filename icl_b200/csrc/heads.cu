@@ -5,6 +5,10 @@
 // All are bandwidth/latency bound: coalesced streaming + warp-shuffle reductions, fp32 math.
 #include "common.cuh"
 
+// scratch of the chunked two-stage reductions in this file (see the section before dwconv3d_wgrad_partial_k)
+#define RED_CHUNKS 296
+#define RED_WS_BYTES (RED_CHUNKS * 16 * 32 * 8)
+
 // ------------------------------------------------------------------------------------------
 // LayerNorm over the last axis, one block per row.
 // ------------------------------------------------------------------------------------------
@@ -155,10 +159,193 @@ __global__ void __launch_bounds__(256) proxy_av_k(const float* __restrict__ map,
   }
   if (threadIdx.x == 0) { mstat[blockIdx.x * 2] = mx; mstat[blockIdx.x * 2 + 1] = se; }
 }
+// ------------------------------------------------------------------------------------------
+// head_dim 16 form (every ICL head of the reference: C / heads = 16) with the voxel axis split over blocks.  The reductions over
+// N — softmax statistics, softmax(map) @ v, and dq = dl^T k in backward — are "weighted column sums" sum_n w[n] * X[n, 0:16]
+// computed per chunk of PA_CH voxels (grid = chunks x (b,h,k): 224 blocks at 24^3, K = 2, where one block per (b,h,k) gives 16)
+// and added in a fixed order by a small combine kernel.  The softmax max comes from per-chunk maxima written by the logits
+// kernel, so chunk partials add without rescaling; backward needs no pass for sum_n p[n] dP[n]: it equals <dxv, xv>.
+// ------------------------------------------------------------------------------------------
+#define PA_HD 16
+#define PA_CH 1024
+__device__ __forceinline__ void load16(const float* __restrict__ p, float* r) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) { const float4 t = reinterpret_cast<const float4*>(p)[q]; r[4 * q] = t.x; r[4 * q + 1] = t.y; r[4 * q + 2] = t.z; r[4 * q + 3] = t.w; }
+}
+__global__ void __launch_bounds__(256) proxy_logits16_k(const float* __restrict__ ql, const float* __restrict__ kv, float* __restrict__ map,
+                                                        float* __restrict__ pmax, int B, int N, int C, int H, int K, float scale, int chunks) {
+  __shared__ float qs[16 * PA_HD];
+  __shared__ float red[8][16];
+  const int b = blockIdx.z, h = blockIdx.y, chunk = blockIdx.x;
+  for (int i = threadIdx.x; i < K * PA_HD; i += 256) qs[i] = ql[(long long)b * K * C + (long long)h * K * PA_HD + i];
+  __syncthreads();
+  float mx[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) mx[k] = -INFINITY;
+  const int n1 = min(N, (chunk + 1) * PA_CH);
+  for (int n = chunk * PA_CH + threadIdx.x; n < n1; n += 256) {
+    float kr[PA_HD];
+    load16(kv + ((long long)b * N + n) * 2 * C + h * PA_HD, kr);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (k < K) {
+      float sacc = 0.f;
+#pragma unroll
+      for (int d = 0; d < PA_HD; ++d) sacc = fmaf(qs[k * PA_HD + d], kr[d], sacc);
+      sacc *= scale;
+      map[(((long long)b * K + k) * H + h) * N + n] = sacc;
+      mx[k] = fmaxf(mx[k], sacc);
+    }
+  }
+  if (pmax) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 16; ++k) if (k < K) { const float m = warp_max(mx[k]); if (lane == 0) red[wid][k] = m; }
+    __syncthreads();
+    if (threadIdx.x < K) {
+      float m = -INFINITY;
+      for (int w = 0; w < 8; ++w) m = fmaxf(m, red[w][threadIdx.x]);
+      pmax[((long long)(b * H + h) * K + threadIdx.x) * chunks + chunk] = m;
+    }
+  }
+}
+// part[bhk][chunk][0..15] = sum_n w[n] * X[n][0:16], part[..][16] = sum_n w[n]
+//   MODE 0: w = exp(map[n] - max over the chunk maxima), X = v (x_off = C)       MODE 1: w = wsrc[n] (dl), X = k (x_off = 0)
+template <int MODE>
+__global__ void __launch_bounds__(256) proxy_wsum16_k(const float* __restrict__ wsrc, const float* __restrict__ kv, int x_off,
+                                                      const float* __restrict__ pmax, float* __restrict__ part, int B, int N, int C, int H, int K,
+                                                      int chunks) {
+  __shared__ float red[8][17];
+  const int bhk = blockIdx.y, chunk = blockIdx.x;
+  const int k = bhk % K, h = (bhk / K) % H, b = bhk / (K * H);
+  float gmax = 0.f;
+  if (MODE == 0) {
+    gmax = -INFINITY;
+    for (int c = 0; c < chunks; ++c) gmax = fmaxf(gmax, pmax[(long long)bhk * chunks + c]);
+  }
+  const float* row = wsrc + (((long long)b * K + k) * H + h) * N;
+  float acc[PA_HD], se = 0.f;
+#pragma unroll
+  for (int d = 0; d < PA_HD; ++d) acc[d] = 0.f;
+  const int n1 = min(N, (chunk + 1) * PA_CH);
+  for (int n = chunk * PA_CH + threadIdx.x; n < n1; n += 256) {
+    const float wv = MODE == 0 ? __expf(row[n] - gmax) : row[n];
+    float xr[PA_HD];
+    load16(kv + ((long long)b * N + n) * 2 * C + x_off + h * PA_HD, xr);
+    se += wv;
+#pragma unroll
+    for (int d = 0; d < PA_HD; ++d) acc[d] = fmaf(wv, xr[d], acc[d]);
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int d = 0; d < PA_HD; ++d) { const float t = warp_sum(acc[d]); if (lane == 0) red[wid][d] = t; }
+  { const float t = warp_sum(se); if (lane == 0) red[wid][16] = t; }
+  __syncthreads();
+  if (threadIdx.x < 17) {
+    float t = 0.f;
+    for (int w = 0; w < 8; ++w) t += red[w][threadIdx.x];
+    part[((long long)bhk * chunks + chunk) * 17 + threadIdx.x] = t;
+  }
+}
+// MODE 0: xv[b, (h*K + k)*16 + d] = sum_c part[d] / sum_c part[16]; mstat[bhk] = (max, sum exp).   MODE 1: dql[...] = scale * sum_c part[d]
+template <int MODE>
+__global__ void proxy_combine16_k(const float* __restrict__ part, const float* __restrict__ pmax, float* __restrict__ out, float* __restrict__ mstat,
+                                  int BHK, int H, int K, int C, int chunks, float scale) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= BHK * PA_HD) return;
+  const int bhk = i / PA_HD, d = i % PA_HD;
+  const int k = bhk % K, h = (bhk / K) % H, b = bhk / (K * H);
+  float a = 0.f, se = 0.f;
+  for (int c = 0; c < chunks; ++c) { a += part[((long long)bhk * chunks + c) * 17 + d]; se += part[((long long)bhk * chunks + c) * 17 + 16]; }
+  const long long o = (long long)b * K * C + ((long long)h * K + k) * PA_HD + d;
+  if (MODE == 0) {
+    out[o] = a / se;
+    if (d == 0) {
+      float gmax = -INFINITY;
+      for (int c = 0; c < chunks; ++c) gmax = fmaxf(gmax, pmax[(long long)bhk * chunks + c]);
+      mstat[2 * bhk] = gmax; mstat[2 * bhk + 1] = se;
+    }
+  } else {
+    out[o] = a * scale;
+  }
+}
+// backward per voxel (thread per (b, n, h)): dl[k, n] = dmap + p (dP - <dxv, xv>), dk = scale * sum_k dl q_k, dv = sum_k p dxv_k
+__global__ void __launch_bounds__(256) proxy_bwd_vox16_k(const float* __restrict__ dmap, const float* __restrict__ dxv, const float* __restrict__ xv,
+                                                         const float* __restrict__ map, const float* __restrict__ ql, const float* __restrict__ kv,
+                                                         const float* __restrict__ mstat, float* __restrict__ dl, float* __restrict__ dkv, int B,
+                                                         int N, int C, int H, int K, float scale) {
+  __shared__ float qs[16 * PA_HD], gs[16 * PA_HD], ms[32], Ds[16];
+  const int b = blockIdx.z, h = blockIdx.y;
+  for (int i = threadIdx.x; i < K * PA_HD; i += 256) {
+    qs[i] = ql[(long long)b * K * C + (long long)h * K * PA_HD + i];
+    gs[i] = dxv ? dxv[(long long)b * K * C + (long long)h * K * PA_HD + i] : 0.f;
+  }
+  if (threadIdx.x < K) {
+    const int id = (b * H + h) * K + threadIdx.x;
+    ms[2 * threadIdx.x] = mstat ? mstat[id * 2] : 0.f;
+    ms[2 * threadIdx.x + 1] = mstat ? 1.f / mstat[id * 2 + 1] : 0.f;
+    float dsum = 0.f;
+    if (dxv) {
+      const long long o = (long long)b * K * C + ((long long)h * K + threadIdx.x) * PA_HD;
+      for (int d = 0; d < PA_HD; ++d) dsum = fmaf(dxv[o + d], xv[o + d], dsum);
+    }
+    Ds[threadIdx.x] = dsum;
+  }
+  __syncthreads();
+  for (int n = blockIdx.x * 256 + threadIdx.x; n < N; n += gridDim.x * 256) {
+    float kr[PA_HD], vr[PA_HD], dk[PA_HD], dv[PA_HD];
+    const float* base = kv + ((long long)b * N + n) * 2 * C + h * PA_HD;
+    load16(base, kr);
+    if (dxv) load16(base + C, vr);
+#pragma unroll
+    for (int d = 0; d < PA_HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int k = 0; k < K; ++k) {
+      const long long o = (((long long)b * K + k) * H + h) * N + n;
+      float g = dmap ? dmap[o] : 0.f;
+      if (dxv) {
+        const float p = __expf(map[o] - ms[2 * k]) * ms[2 * k + 1];
+        float dP = 0.f;
+#pragma unroll
+        for (int d = 0; d < PA_HD; ++d) dP = fmaf(gs[k * PA_HD + d], vr[d], dP);
+        g += p * (dP - Ds[k]);
+#pragma unroll
+        for (int d = 0; d < PA_HD; ++d) dv[d] = fmaf(p, gs[k * PA_HD + d], dv[d]);
+      }
+      dl[o] = g;
+      const float gsc = g * scale;
+#pragma unroll
+      for (int d = 0; d < PA_HD; ++d) dk[d] = fmaf(gsc, qs[k * PA_HD + d], dk[d]);
+    }
+    float* o = dkv + ((long long)b * N + n) * 2 * C + h * PA_HD;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      reinterpret_cast<float4*>(o)[q] = make_float4(dk[4 * q], dk[4 * q + 1], dk[4 * q + 2], dk[4 * q + 3]);
+      reinterpret_cast<float4*>(o + C)[q] = make_float4(dv[4 * q], dv[4 * q + 1], dv[4 * q + 2], dv[4 * q + 3]);
+    }
+  }
+}
+static inline bool proxy16_ok(int C, int H, int K, int N, float* ws) {
+  const int chunks = cdiv(N, PA_CH);
+  return ws != nullptr && C % H == 0 && C / H == PA_HD && K <= 16 && C % 4 == 0 && (long long)chunks * 18 * 4 <= RED_WS_BYTES;
+}
+
 ICL_API int icl_proxy_attn_fwd(const float* ql, const float* kv, float* map, float* xv, float* mstat, int B, int N, int C, int H, int K,
-                               float scale, int want_xv, void* stream) {
+                               float scale, int want_xv, float* ws, void* stream) {
   const int hd = C / H;
   ICL_REQUIRE(C % H == 0 && hd <= PA_MAXHD, "proxy_attn: head_dim %d unsupported (max %d)", hd, PA_MAXHD);
+  const int chunks = cdiv(N, PA_CH), BHK = B * H * K;
+  if (proxy16_ok(C, H, K, N, ws) && (long long)BHK * chunks * 18 * 4 <= RED_WS_BYTES) {
+    float* pmax = ws;
+    float* part = ws + (long long)BHK * chunks;
+    proxy_logits16_k<<<dim3(chunks, H, B), 256, 0, as_stream(stream)>>>(ql, kv, map, want_xv ? pmax : nullptr, B, N, C, H, K, scale, chunks);
+    icl_count_launch(1);
+    if (want_xv) {
+      proxy_wsum16_k<0><<<dim3(chunks, BHK), 256, 0, as_stream(stream)>>>(map, kv, C, pmax, part, B, N, C, H, K, chunks);
+      icl_count_launch(1);
+      proxy_combine16_k<0><<<cdiv(BHK * PA_HD, 128), 128, 0, as_stream(stream)>>>(part, pmax, xv, mstat, BHK, H, K, C, chunks, scale);
+      icl_count_launch(1);
+    }
+    return icl_check_launch("proxy_attn_fwd");
+  }
   proxy_logits_k<<<dim3(cdiv(N, 256), H, B), 256, K * hd * sizeof(float), as_stream(stream)>>>(ql, kv, map, B, N, C, H, K, scale);
   icl_count_launch(1);
   if (want_xv) {
@@ -256,11 +443,23 @@ __global__ void __launch_bounds__(256) proxy_bwd2_k(const float* __restrict__ dl
     for (int d = 0; d < hd; ++d) { o[d] = dk[d]; o[C + d] = dv[d]; }
   }
 }
-ICL_API int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* map, const float* ql, const float* kv, const float* mstat,
-                               float* dl_scratch, float* dql, float* dkv, int B, int N, int C, int H, int K, float scale, void* stream) {
+ICL_API int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* xv, const float* map, const float* ql, const float* kv,
+                               const float* mstat, float* dl_scratch, float* dql, float* dkv, int B, int N, int C, int H, int K, float scale,
+                               float* ws, void* stream) {
   const int hd = C / H;
   ICL_REQUIRE(C % H == 0 && hd <= PA_MAXHD, "proxy_attn_bwd: head_dim %d unsupported", hd);
   ICL_REQUIRE(dxv == nullptr || mstat != nullptr, "proxy_attn_bwd: softmax stats required when dxv is given");
+  const int chunks = cdiv(N, PA_CH), BHK = B * H * K;
+  if (proxy16_ok(C, H, K, N, ws) && (long long)BHK * chunks * 18 * 4 <= RED_WS_BYTES && (dxv == nullptr || xv != nullptr)) {
+    float* part = ws + (long long)BHK * chunks;
+    proxy_bwd_vox16_k<<<dim3(cdiv(N, 256), H, B), 256, 0, as_stream(stream)>>>(dmap, dxv, xv, map, ql, kv, mstat, dl_scratch, dkv, B, N, C, H, K, scale);
+    icl_count_launch(1);
+    proxy_wsum16_k<1><<<dim3(chunks, BHK), 256, 0, as_stream(stream)>>>(dl_scratch, kv, 0, nullptr, part, B, N, C, H, K, chunks);
+    icl_count_launch(1);
+    proxy_combine16_k<1><<<cdiv(BHK * PA_HD, 128), 128, 0, as_stream(stream)>>>(part, nullptr, dql, nullptr, BHK, H, K, C, chunks, scale);
+    icl_count_launch(1);
+    return icl_check_launch("proxy_attn_bwd");
+  }
   proxy_bwd1_k<<<B * H * K, 256, 0, as_stream(stream)>>>(dmap, dxv, map, kv, mstat, dl_scratch, dql, B, N, C, H, K, scale);
   icl_count_launch(1);
   proxy_bwd2_k<<<dim3(cdiv(N, 256), H, B), 256, (2 * K * hd + 2 * K) * sizeof(float), as_stream(stream)>>>(
@@ -305,8 +504,6 @@ ICL_API int icl_dwconv3d(const float* x, const float* w, float* y, int NB, int C
 // partial sums to a workspace and a small second kernel adds the partials in a fixed order (deterministic).
 // `ws` arguments: device scratch of at least ICL_RED_WS_BYTES bytes (icl_reduce_workspace_bytes()).
 // ------------------------------------------------------------------------------------------
-#define RED_CHUNKS 296
-#define RED_WS_BYTES (RED_CHUNKS * 16 * 32 * 8)
 ICL_API int icl_reduce_workspace_bytes(void) { return RED_WS_BYTES; }
 
 static inline int red_chunks(long long n, int per_chunk_min) {

@@ -118,24 +118,26 @@ class ProxyAttnFn(torch.autograd.Function):
         xv = torch.empty((B, K, C), dtype=torch.float32, device=ql.device) if want_xv else None
         mstat = torch.empty((B * H * K, 2), dtype=torch.float32, device=ql.device) if want_xv else None
         call("icl_proxy_attn_fwd", P(ql_), P(kv_), P(amap), P(xv), P(mstat), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K),
-             c_f(scale), c_int(1 if want_xv else 0), mbytes=4e-6 * (B * N * C * (2 if want_xv else 1) + B * K * H * N),
+             c_f(scale), c_int(1 if want_xv else 0), P(ops.reduce_ws(ql.device)), mbytes=4e-6 * (B * N * C * (2 if want_xv else 1) + B * K * H * N),
              tag="B%d N%d C%d H%d K%d" % (B, N, C, H, K))
-        ctx.save_for_backward(ql_, kv_, amap, mstat)
+        ctx.save_for_backward(ql_, kv_, amap, mstat, xv)
         ctx.dims = (B, N, C, H, K, scale)
         ctx.set_materialize_grads(False)
         return xv, amap
 
     @staticmethod
     def backward(ctx, dxv, dmap):
-        ql_, kv_, amap, mstat = ctx.saved_tensors
+        ql_, kv_, amap, mstat, xv = ctx.saved_tensors
         B, N, C, H, K, scale = ctx.dims
         if dxv is None and dmap is None:
             return None, None, None, None
         dl = torch.empty_like(amap)
         dql = torch.empty_like(ql_)
         dkv = torch.empty_like(kv_)
-        call("icl_proxy_attn_bwd", P(None if dmap is None else _c(dmap)), P(None if dxv is None else _c(dxv)), P(amap), P(ql_), P(kv_),
-             P(mstat), P(dl), P(dql), P(dkv), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K), c_f(scale),
+        dmap_c = None if dmap is None else _c(dmap)   # keep the (possibly fresh) contiguous copies alive across the launch
+        dxv_c = None if dxv is None else _c(dxv)
+        call("icl_proxy_attn_bwd", P(dmap_c), P(dxv_c), P(xv), P(amap), P(ql_), P(kv_),
+             P(mstat), P(dl), P(dql), P(dkv), c_int(B), c_int(N), c_int(C), c_int(H), c_int(K), c_f(scale), P(ops.reduce_ws(ql_.device)),
              mbytes=4e-6 * (2 * B * N * 2 * C + 3 * B * K * H * N), tag="B%d N%d C%d H%d K%d" % (B, N, C, H, K))
         return dql, dkv, None, None
 

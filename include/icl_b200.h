@@ -128,10 +128,13 @@ int icl_layernorm_bwd(const float* dy, const float* x, const float* w, const flo
                       int C, void* stream);
 
 /* ---- Query_Attention (voxel -> class-proxy cross attention): networks/unet_3D_icl.py:283-297 ---- */
+/* `ws`: device scratch of icl_reduce_workspace_bytes() bytes (per-chunk partial sums of the split-N reductions); `xv` in backward is
+ * the forward output (sum_n p dP equals <dxv, xv>, so backward needs no reduction pass for it) */
 int icl_proxy_attn_fwd(const float* ql, const float* kv, float* map, float* xv, float* mstat, int B, int N, int C, int H, int K, float scale,
-                       int want_xv, void* stream);
-int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* map, const float* ql, const float* kv, const float* mstat,
-                       float* dl_scratch, float* dql, float* dkv, int B, int N, int C, int H, int K, float scale, void* stream);
+                       int want_xv, float* ws, void* stream);
+int icl_proxy_attn_bwd(const float* dmap, const float* dxv, const float* xv, const float* map, const float* ql, const float* kv,
+                       const float* mstat, float* dl_scratch, float* dql, float* dkv, int B, int N, int C, int H, int K, float scale,
+                       float* ws, void* stream);
 
 /* ---- SeparableConv3d (depthwise 3^3 + BatchNorm3d(train) + ReLU + pointwise + BN + ReLU): networks/unet_3D_icl.py:317-345 ---- */
 int icl_dwconv3d(const float* x, const float* w, float* y, int NB, int CH, int d, int h, int wd, int flip, void* stream);

@@ -402,7 +402,9 @@ def test_layernorm(rows, C):
     assert_close(bc.grad.cpu(), gb, 3e-5, "ln db")
 
 
-@pytest.mark.parametrize("B,N,C,H,K", [(2, 216, 64, 4, 3), (1, 500, 32, 2, 16), (2, 64, 16, 1, 2)])
+# head_dim 16 takes the split-N kernels (N = 2500: three voxel chunks); (1, 300, 64, 2, 3) has head_dim 32: the generic kernels
+@pytest.mark.parametrize("B,N,C,H,K", [(2, 216, 64, 4, 3), (1, 500, 32, 2, 16), (2, 64, 16, 1, 2), (2, 2500, 64, 4, 2), (1, 3000, 32, 2, 16),
+                                       (1, 300, 64, 2, 3)])
 def test_proxy_attention(B, N, C, H, K):
     import icl_b200.functional as Fn
     hd = C // H
