@@ -43,6 +43,7 @@
 struct WgradParams {
   float* partial;
   int B, D, H, W;
+  int Bx;  // samples the X tensor was ALLOCATED with (its precision-plane stride); B <= Bx samples from its front are used
   int n_co_tiles;
   int tiles_h, tiles_w, zsteps;
   int items, splits;
@@ -102,7 +103,7 @@ conv3d_wgrad_umma_k(const __grid_constant__ CUtensorMap mapX, const __grid_const
         mbar_expect_tx(fb, stage_bytes);
         for (int pl = 0; pl < P; ++pl) {
           // X planes 2*zs-1 .. 2*zs+2 (out-of-range planes / halo rows / halo columns zero-fill)
-          tma_load_4d(sa + pl * WG_A_BYTES, &mapX, fb, (w.w0 - 1) * 8, w.h0 - 1, 2 * w.zs - 1, (pl * p.B + w.b) * p.Ci8 + ci_tile * 2);
+          tma_load_4d(sa + pl * WG_A_BYTES, &mapX, fb, (w.w0 - 1) * 8, w.h0 - 1, 2 * w.zs - 1, (pl * p.Bx + w.b) * p.Ci8 + ci_tile * 2);
           // dY planes 2*zs, 2*zs+1
           tma_load_4d(sa + a_bytes + pl * WG_B_BYTES, &mapY, fb, w.w0 * 8, w.h0, 2 * w.zs, (pl * p.B + w.b) * p.Co8 + co_tile * 2);
         }
@@ -234,12 +235,14 @@ ICL_API int icl_conv3d_wgrad_umma_slots(int Cin, int Cout, int B, int D, int H, 
 }
 
 ICL_API int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, int Cout, float* dw, int Cin_total, int ci_off, float* workspace,
-                                  int B, int D, int H, int W, int P, int accumulate, void* stream) {
+                                  int B, int D, int H, int W, int P, int accumulate, int Bx, void* stream) {
   ICL_REQUIRE(Cin > 0 && Cin % 16 == 0 && Cout % 16 == 0, "conv3d_wgrad_umma: channels must be multiples of 16 (Cin=%d Cout=%d)", Cin, Cout);
   ICL_REQUIRE(D % 2 == 0, "conv3d_wgrad_umma: depth %d must be even", D);
   ICL_REQUIRE(P == 1 || P == 2, "conv3d_wgrad_umma: P must be 1 or 2");
   WgradParams p;
-  p.partial = workspace; p.B = B; p.D = D; p.H = H; p.W = W;
+  if (Bx <= 0) Bx = B;
+  ICL_REQUIRE(Bx >= B, "conv3d_wgrad_umma: Bx=%d < B=%d", Bx, B);
+  p.partial = workspace; p.B = B; p.Bx = Bx; p.D = D; p.H = H; p.W = W;
   p.n_co_tiles = Cout / 16;
   p.tiles_h = cdiv(H, WG_TH); p.tiles_w = cdiv(W, WG_TW); p.zsteps = D / 2;
   p.items = B * p.zsteps * p.tiles_h * p.tiles_w;
@@ -252,7 +255,7 @@ ICL_API int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, 
   if (stages > WG_MAX_STAGES) stages = WG_MAX_STAGES;
   p.stages = stages;
   CUtensorMap mx, my;
-  if (make_wg_map(&mx, x_pk, P, B, Cin, D, H, W, WG_HW, WG_HL, WG_PX)) return -1;
+  if (make_wg_map(&mx, x_pk, P, Bx, Cin, D, H, W, WG_HW, WG_HL, WG_PX)) return -1;
   if (make_wg_map(&my, dy_pk, P, B, Cout, D, H, W, WG_TW, WG_TH, WG_PQ)) return -1;
   const size_t smem = stage_bytes * stages + 128;
   static bool configured = false;

@@ -40,7 +40,7 @@ class _Act:
 
 
 class _Half:
-    __slots__ = ("srcs", "w", "y", "mr", "out", "umma", "owner")
+    __slots__ = ("srcs", "w", "y", "mr", "out", "umma", "owner", "pk_bs")
 
 
 def _half_fwd(srcs, w, b, owner=None):
@@ -51,7 +51,7 @@ def _half_fwd(srcs, w, b, owner=None):
     B, D, H, W, _ = srcs[0].shape
     stats = ops.zeros((B, cout, 2), torch.float64, w.device)
     h = _Half()
-    h.srcs, h.w, h.owner = srcs, w, owner
+    h.srcs, h.w, h.owner, h.pk_bs = srcs, w, owner, 0
     h.umma = ops.umma_ok(cins, cout) and all(s.pk is not None for s in srcs)
     if h.umma:
         h.y = ops.conv3d_umma([s.pk for s in srcs], cins, ops.pack_w_umma_cached(w, False, D, owner), b, cout, B, D, H, W, stats)
@@ -65,8 +65,21 @@ def _half_fwd(srcs, w, b, owner=None):
     return h
 
 
-def _half_bwd(h, dA, need_dx):
-    """Returns (dw, db, [dx per source] or None)."""
+def _half_prefix(h, n):
+    """The first n samples of a recorded conv half (batch-major fp32 tensors are contiguous prefixes; the PK operands stay the
+    full tensors and are read with their allocated batch as plane stride, `pk_bs`)."""
+    if n == h.y.shape[0]:
+        return h
+    q = _Half()
+    q.srcs = [_Act(None if s.f32 is None else s.f32[:n], s.pk, (n,) + tuple(s.shape[1:])) for s in h.srcs]
+    q.w, q.owner, q.umma, q.out = h.w, h.owner, h.umma, None
+    q.y, q.mr = h.y[:n], h.mr[:n]
+    q.pk_bs = h.y.shape[0]
+    return q
+
+
+def _half_bwd(h, dA, need_dx, dx_out0=None):
+    """Returns (dw, db, [dx per source] or None).  dx_out0: optional preallocated tensor for the gradient of the FIRST source."""
     cins = [s.C for s in h.srcs]
     cout = h.w.shape[0]
     B, D, H, W, _ = h.y.shape
@@ -75,7 +88,7 @@ def _half_bwd(h, dA, need_dx):
     if wgrad_umma:
         # fp32 dY is only read by the CUDA-core data-gradient fallback
         dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True, want_f32=need_dx and not dgrad_umma)
-        dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W)
+        dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W, bx=h.pk_bs)
     elif ops.stem_ok(cins, cout):
         dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma, want_dbias=True)
         dw = ops.conv3d_stem_wgrad(h.srcs[0].f32, dY, B, D, H, W)
@@ -88,12 +101,19 @@ def _half_bwd(h, dA, need_dx):
     if dgrad_umma:
         wp = ops.pack_w_umma_cached(h.w, True, D, h.owner)
         if len(cins) == 2:
-            d0, d1 = ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W, split=cins[0])
+            d0, d1 = ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W, split=cins[0], out=dx_out0)
             return dw, db, [d0, d1]
-        return dw, db, [ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W)]
+        return dw, db, [ops.conv3d_umma([dY_pk], [cout], wp, None, cin_total, B, D, H, W, out=dx_out0)]
     dx = ops.conv3d_direct([dY], [cout], ops.repack_w_f32(h.w, True), None, cin_total, B, D, H, W)
     if len(cins) == 2:
-        return dw, db, [dx[..., :cins[0]].contiguous(), dx[..., cins[0]:].contiguous()]
+        d0 = dx[..., :cins[0]].contiguous()
+        if dx_out0 is not None:
+            dx_out0.copy_(d0)
+            d0 = dx_out0
+        return dw, db, [d0, dx[..., cins[0]:].contiguous()]
+    if dx_out0 is not None:
+        dx_out0.copy_(dx)
+        dx = dx_out0
     return dw, db, [dx]
 
 
@@ -103,10 +123,13 @@ def _block_fwd(srcs, p, owners=(None, None)):
     return (h1, h2)
 
 
-def _block_bwd(blk, dA, need_dx):
+def _block_bwd(blk, dA, need_dx, n=None, dx_out0=None):
+    """n: run on the first n samples only (labeled prefix of a batched labeled + unlabeled pass)."""
     h1, h2 = blk
+    if n is not None:
+        h1, h2 = _half_prefix(h1, n), _half_prefix(h2, n)
     dw2, db2, dx2 = _half_bwd(h2, dA, True)
-    dw1, db1, dx1 = _half_bwd(h1, dx2[0], need_dx)
+    dw1, db1, dx1 = _half_bwd(h1, dx2[0], need_dx, dx_out0)
     return [dw1, db1, dw2, db2], dx1
 
 
@@ -119,6 +142,65 @@ def _add(a, b):
     return a
 
 
+def _forward_body(ctx, x, drop_cfg, params):
+    """Forward of the whole backbone on the batch x; records everything backward needs on ctx.  Returns the NDHWC tensors
+    (final logits, center after dropout1, up4, up3)."""
+    ctx.set_materialize_grads(False)
+    p = [t.detach() for t in params]
+    blk = {name: p[4 * i:4 * i + 4] for i, name in enumerate(PARAM_BLOCKS)}
+    own = {name: (params[4 * i], params[4 * i + 2]) for i, name in enumerate(PARAM_BLOCKS)}   # weight Parameters of conv1 / conv2
+    wf, bf = p[36], p[37]
+    x_ = ops.to_ndhwc(x.detach())
+    B, D, H, W, Cin = x_.shape
+    # every conv from the second one on runs on the tensor cores when all channel counts are multiples of 16:
+    # pooled / upsampled tensors are then only ever read as PK operands and their fp32 copies are not written
+    # (the tensor-core weight gradient needs an even depth at every level: with D % 32 != 0 the `center` level has an odd
+    # depth, its weight gradient runs on the CUDA-core kernel and reads the fp32 copies, so they must exist)
+    lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16, D // 16)
+    if D % 16 or H % 16 or W % 16:
+        raise RuntimeError("unet_3D backbone: spatial size must be a multiple of 16, got %s" % ((D, H, W),))
+    rec = {}
+    a0 = _Act(x_, ops.pack_pk(x_) if ops.pk_ok(Cin) else None)
+    enc = a0
+    for i, name in enumerate(["conv1", "conv2", "conv3", "conv4"]):
+        rec[name] = _block_fwd([enc], blk[name], own[name])
+        out = rec[name][1].out
+        pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C), want_f32=not lean)
+        rec["pool%d" % (i + 1)] = idx
+        enc = _Act(pooled, ppk, (B, out.shape[1] // 2, out.shape[2] // 2, out.shape[3] // 2, out.C))
+    rec["center"] = _block_fwd([enc], blk["center"], own["center"])
+    center = rec["center"][1].out
+    if drop_cfg is not None:
+        pdrop, m1, m2, s1, s2 = drop_cfg
+        cd = ops.dropout(center.f32, pdrop, m1, s1)
+        center_d = _Act(cd, ops.pack_pk(cd) if ops.pk_ok(center.C) else None)
+    else:
+        center_d = center
+    coarse = center_d
+    for name, skip in (("up_concat4.conv", "conv4"), ("up_concat3.conv", "conv3"), ("up_concat2.conv", "conv2"),
+                       ("up_concat1.conv", "conv1")):
+        up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
+        cs = coarse.shape
+        rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name])
+        coarse = rec[name][1].out
+    up1 = coarse
+    up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32
+    K = wf.shape[0]
+    rows = B * D * H * W
+    final = torch.empty((B, D, H, W, K), dtype=torch.float32, device=x_.device)
+    wf2 = wf.reshape(K, -1)
+    if wf2.shape[1] == 16 and K <= 16:
+        ops.call("icl_head1x1_fwd", ops.P(up1d), ops.P(wf2), ops.P(bf), ops.P(final), ops.c_ll(rows), ops.c_int(16), ops.c_int(K),
+                 mbytes=4e-6 * rows * (16 + K))
+    else:
+        ops.sgemm(rows, K, wf2.shape[1], up1d, wf2.shape[1], 1, wf2, 1, wf2.shape[1], final, K, 1, bias=bf, bias_mode=1)
+    rec["up1d"] = up1d
+    ctx.rec, ctx.blk, ctx.wf, ctx.drop_cfg = rec, blk, wf2, drop_cfg
+    ctx.needs_x = x.requires_grad
+    return (final, center_d.f32, rec["up_concat4.conv"][1].out.f32, rec["up_concat3.conv"][1].out.f32)
+
+
+
 class Backbone3DFn(torch.autograd.Function):
     """(x, drop_cfg, *38 params) -> (final [B,K,D,H,W], center_drop, up4, up3), all channels_last_3d views.
 
@@ -127,59 +209,7 @@ class Backbone3DFn(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, drop_cfg, *params):
-        ctx.set_materialize_grads(False)
-        p = [t.detach() for t in params]
-        blk = {name: p[4 * i:4 * i + 4] for i, name in enumerate(PARAM_BLOCKS)}
-        own = {name: (params[4 * i], params[4 * i + 2]) for i, name in enumerate(PARAM_BLOCKS)}   # weight Parameters of conv1 / conv2
-        wf, bf = p[36], p[37]
-        x_ = ops.to_ndhwc(x.detach())
-        B, D, H, W, Cin = x_.shape
-        # every conv from the second one on runs on the tensor cores when all channel counts are multiples of 16:
-        # pooled / upsampled tensors are then only ever read as PK operands and their fp32 copies are not written
-        # (the tensor-core weight gradient needs an even depth at every level: with D % 32 != 0 the `center` level has an odd
-        # depth, its weight gradient runs on the CUDA-core kernel and reads the fp32 copies, so they must exist)
-        lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16, D // 16)
-        if D % 16 or H % 16 or W % 16:
-            raise RuntimeError("unet_3D backbone: spatial size must be a multiple of 16, got %s" % ((D, H, W),))
-        rec = {}
-        a0 = _Act(x_, ops.pack_pk(x_) if ops.pk_ok(Cin) else None)
-        enc = a0
-        for i, name in enumerate(["conv1", "conv2", "conv3", "conv4"]):
-            rec[name] = _block_fwd([enc], blk[name], own[name])
-            out = rec[name][1].out
-            pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C), want_f32=not lean)
-            rec["pool%d" % (i + 1)] = idx
-            enc = _Act(pooled, ppk, (B, out.shape[1] // 2, out.shape[2] // 2, out.shape[3] // 2, out.C))
-        rec["center"] = _block_fwd([enc], blk["center"], own["center"])
-        center = rec["center"][1].out
-        if drop_cfg is not None:
-            pdrop, m1, m2, s1, s2 = drop_cfg
-            cd = ops.dropout(center.f32, pdrop, m1, s1)
-            center_d = _Act(cd, ops.pack_pk(cd) if ops.pk_ok(center.C) else None)
-        else:
-            center_d = center
-        coarse = center_d
-        for name, skip in (("up_concat4.conv", "conv4"), ("up_concat3.conv", "conv3"), ("up_concat2.conv", "conv2"),
-                           ("up_concat1.conv", "conv1")):
-            up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
-            cs = coarse.shape
-            rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name])
-            coarse = rec[name][1].out
-        up1 = coarse
-        up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32
-        K = wf.shape[0]
-        rows = B * D * H * W
-        final = torch.empty((B, D, H, W, K), dtype=torch.float32, device=x_.device)
-        wf2 = wf.reshape(K, -1)
-        if wf2.shape[1] == 16 and K <= 16:
-            ops.call("icl_head1x1_fwd", ops.P(up1d), ops.P(wf2), ops.P(bf), ops.P(final), ops.c_ll(rows), ops.c_int(16), ops.c_int(K),
-                     mbytes=4e-6 * rows * (16 + K))
-        else:
-            ops.sgemm(rows, K, wf2.shape[1], up1d, wf2.shape[1], 1, wf2, 1, wf2.shape[1], final, K, 1, bias=bf, bias_mode=1)
-        rec["up1d"] = up1d
-        ctx.rec, ctx.blk, ctx.wf, ctx.drop_cfg = rec, blk, wf2, drop_cfg
-        ctx.needs_x = x.requires_grad
-        outs = (final, center_d.f32, rec["up_concat4.conv"][1].out.f32, rec["up_concat3.conv"][1].out.f32)
+        outs = _forward_body(ctx, x, drop_cfg, params)
         return tuple(ops.to_ncdhw_view(o) for o in outs)
 
     @staticmethod
@@ -257,3 +287,152 @@ class Backbone3DFn(torch.autograd.Function):
         out += grads.get("final", [None, None])
         ctx.rec = None
         return (dx_in, None) + tuple(out)
+
+
+def _head_bwd(gf, up1d, wf2):
+    """Backward of the `final` 1x1x1 conv on NDHWC tensors: returns (d_up1d, [dW, db])."""
+    B, D, H, W, K = gf.shape
+    rows, C1 = B * D * H * W, wf2.shape[1]
+    d_up1d = torch.empty((B, D, H, W, C1), dtype=torch.float32, device=gf.device)
+    if C1 == 16 and K in (1, 2, 4, 16):
+        dwf = ops.zeros((K, C1), torch.float32, gf.device)
+        dbf = ops.zeros((K,), torch.float32, gf.device)
+        ops.call("icl_head1x1_bwd", ops.P(gf), ops.P(up1d), ops.P(wf2), ops.P(d_up1d), ops.P(dwf), ops.P(dbf), ops.c_ll(rows),
+                 ops.c_int(16), ops.c_int(K), mbytes=4e-6 * rows * (32 + K))
+    else:
+        ops.sgemm(rows, C1, K, gf, K, 1, wf2, C1, 1, d_up1d, C1, 1)
+        dwf = torch.empty((K, C1), dtype=torch.float32, device=gf.device)
+        ops.sgemm(K, C1, rows, gf, 1, K, up1d, C1, 1, dwf, C1, 1)
+        dbf = torch.empty((K,), dtype=torch.float32, device=gf.device)
+        ops.call("icl_colsum", ops.P(gf), ops.P(dbf), ops.c_ll(rows), ops.c_int(K), ops.c_int(0), tag="%dx%d" % (rows, K))
+    return d_up1d, [dwf.reshape(K, C1, 1, 1, 1), dbf]
+
+
+class BackbonePairFn(torch.autograd.Function):
+    """The labeled and the unlabeled pass of unet_3D_icl.forward (unet_3D_icl.py:100-139) as ONE batched backbone pass:
+    (x = cat([x_lab, x_unlab]), n_lab, drop_cfg, *38 params) ->
+    (final_lab, final_unlab, center_lab, center_unlab, up4_lab, up4_unlab, up3_lab, up3_unlab).
+
+    Exact: InstanceNorm is per sample and both passes use the same weights, so batching changes no value — it halves the launches
+    of the forward pass and doubles the tiles per convolution launch.  Backward reproduces the reference's pruning with sub-batches
+    instead of two autograd nodes: `final`, up_concat1 and up_concat2 run on the samples whose logits received a gradient (the
+    labeled prefix: final_unlab is only ever used detached), the layers both branches reach (up_concat3/4, center,
+    encoder) run once on the whole batch with the per-branch gradients assembled per row range.  Parameter gradients are the sums
+    over the samples that took part, i.e. exactly what autograd accumulates from the reference's two passes."""
+
+    @staticmethod
+    def forward(ctx, x, n_lab, drop_cfg, *params):
+        final, center, up4, up3 = _forward_body(ctx, x, drop_cfg, params)
+        ctx.n_lab, ctx.B = int(n_lab), final.shape[0]
+        v = ops.to_ncdhw_view
+        n = ctx.n_lab
+        return (v(final[:n]), v(final[n:]), v(center[:n]), v(center[n:]), v(up4[:n]), v(up4[n:]), v(up3[:n]), v(up3[n:]))
+
+    @staticmethod
+    def backward(ctx, gfl, gfu, gcl, gcu, g4l, g4u, g3l, g3u):
+        rec, wf2, drop_cfg, nl, B = ctx.rec, ctx.wf, ctx.drop_cfg, ctx.n_lab, ctx.B
+        grads = {}
+        nd = lambda g: None if g is None else ops.to_ndhwc(g)
+        dev = wf2.device
+
+        def assemble(shape_full, parts):
+            """Full-batch gradient from row-range pieces [(row0, row1, tensor)]; rows nobody covers are zero.  None if no piece.
+            Pieces are cut at the labeled / unlabeled boundary, so every piece covers exactly one of the two segments."""
+            cut = []
+            for a, b_, t in parts:
+                if t is None or a == b_:
+                    continue
+                if a < nl < b_:
+                    cut += [(a, nl, t[:nl - a]), (nl, b_, t[nl - a:])]
+                else:
+                    cut.append((a, b_, t))
+            if not cut:
+                return None
+            out = torch.empty(shape_full, dtype=torch.float32, device=dev)
+            for seg in ((0, nl), (nl, shape_full[0])):
+                if seg[0] == seg[1]:
+                    continue
+                mine = [t for a, b_, t in cut if (a, b_) == seg]
+                if not mine:
+                    out[seg[0]:seg[1]].zero_()
+                    continue
+                out[seg[0]:seg[1]].copy_(mine[0])
+                for t in mine[1:]:
+                    ops.axpby(t.contiguous(), out[seg[0]:seg[1]], 1.0, 1.0)
+            return out
+
+        # ---- head section: final, dropout2, up_concat1, up_concat2 on the samples whose logits carry a gradient
+        gfl, gfu = nd(gfl), nd(gfu)
+        nh = 0
+        if gfu is not None:
+            nh = B
+            gf = assemble((B,) + tuple(gfu.shape[1:]), [(0, nl, gfl), (nl, B, gfu)])
+        elif gfl is not None:
+            nh, gf = nl, gfl
+        d_skip = {"conv1": None, "conv2": None}   # full-batch buffers whose first nh samples hold the skip gradients
+        d_up3_head = None
+        if nh:
+            d_up1d, grads["final"] = _head_bwd(gf, rec["up1d"][:nh], wf2)
+            if drop_cfg is not None:
+                m2 = None if drop_cfg[2] is None else drop_cfg[2][:nh]
+                d_up = ops.dropout(d_up1d, drop_cfg[0], m2, drop_cfg[4])
+            else:
+                d_up = d_up1d
+            for name, skip, below in (("up_concat1.conv", "conv1", "up_concat2.conv"), ("up_concat2.conv", "conv2", "up_concat3.conv")):
+                full = torch.empty(rec[skip][1].out.shape, dtype=torch.float32, device=dev)
+                pg, dxs = _block_bwd(rec[name], d_up, True, n=nh, dx_out0=full[:nh])
+                grads[name] = pg
+                d_skip[skip] = full
+                cs = rec[below][1].out.shape
+                d_up = torch.empty((nh,) + tuple(cs[1:]), dtype=torch.float32, device=dev)
+                ops.upsample2x_bwd(dxs[1], 0, cs[4], d_up, False)
+            d_up3_head = d_up
+
+        # ---- shared section on the whole batch
+        def up_block_bwd(name, dA, coarse_shape):
+            pg, dxs = _block_bwd(rec[name], dA, True)
+            grads[name] = pg
+            dcoarse = torch.empty(coarse_shape, dtype=torch.float32, device=dev)
+            ops.upsample2x_bwd(dxs[1], 0, coarse_shape[4], dcoarse, False)
+            return dxs[0], dcoarse
+
+        s3, s4, sc = rec["up_concat3.conv"][1].out.shape, rec["up_concat4.conv"][1].out.shape, rec["center"][1].out.shape
+        d_c3 = d_c4 = None
+        d_up3 = assemble(tuple(s3), [(0, nl, nd(g3l)), (nl, B, nd(g3u)), (0, nh, d_up3_head)])
+        d_up4_in = d_cd_in = None
+        if d_up3 is not None:
+            d_c3, d_up4_in = up_block_bwd("up_concat3.conv", d_up3, tuple(s4))
+        d_up4 = assemble(tuple(s4), [(0, nl, nd(g4l)), (nl, B, nd(g4u)), (0, B, d_up4_in)])
+        if d_up4 is not None:
+            d_c4, d_cd_in = up_block_bwd("up_concat4.conv", d_up4, tuple(sc))
+        d_cd = assemble(tuple(sc), [(0, nl, nd(gcl)), (nl, B, nd(gcu)), (0, B, d_cd_in)])
+        dx_in = None
+        if d_cd is not None:
+            d_center = ops.dropout(d_cd, drop_cfg[0], drop_cfg[1], drop_cfg[3]) if drop_cfg is not None else d_cd
+            pg, dxs = _block_bwd(rec["center"], d_center, True)
+            grads["center"] = pg
+            d_pool = dxs[0]
+            d_full = {"conv4": d_c4, "conv3": d_c3, "conv2": d_skip["conv2"], "conv1": d_skip["conv1"]}
+            for i, name in reversed(list(enumerate(["conv1", "conv2", "conv3", "conv4"]))):
+                idx = rec["pool%d" % (i + 1)]
+                dc = d_full[name]
+                if dc is None:
+                    dc = torch.empty(rec[name][1].out.shape, dtype=torch.float32, device=dev)
+                    ops.maxpool_bwd(d_pool, idx, dc, False)
+                elif name in ("conv1", "conv2") and nh < B:
+                    # skip gradients exist for the first nh samples only: accumulate there, plain write for the rest
+                    ops.maxpool_bwd(d_pool[:nh], idx[:nh], dc[:nh], True)
+                    ops.maxpool_bwd(d_pool[nh:], idx[nh:], dc[nh:], False)
+                else:
+                    ops.maxpool_bwd(d_pool, idx, dc, True)
+                need_dx = (i > 0) or ctx.needs_x
+                pg, dxs = _block_bwd(rec[name], dc, need_dx)
+                grads[name] = pg
+                d_pool = dxs[0] if dxs is not None else None
+            dx_in = ops.to_ncdhw_view(d_pool) if (ctx.needs_x and d_pool is not None) else None
+        out = []
+        for name in PARAM_BLOCKS:
+            out += grads.get(name, [None, None, None, None])
+        out += grads.get("final", [None, None])
+        ctx.rec = None
+        return (dx_in, None, None) + tuple(out)

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .backbone3d import Backbone3DFn
+from .backbone3d import Backbone3DFn, BackbonePairFn
 from .utils import UnetConv3, UnetUp3_CT, _kaiming
 
 
@@ -58,6 +58,20 @@ class _Backbone3DModule(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("icl_b200 networks run on CUDA tensors only (no CPU fallback)")
         return Backbone3DFn.apply(x, self._drop_cfg(), *self._backbone_params())
+
+    def _run_pair(self, x_lab, x_unlab):
+        """Labeled and unlabeled pass as one batched pass (backbone3d.BackbonePairFn).  Returns
+        ((final, center, up4, up3) of the labeled samples, the same for the unlabeled samples)."""
+        if not (x_lab.is_cuda and x_unlab.is_cuda):
+            raise RuntimeError("icl_b200 networks run on CUDA tensors only (no CPU fallback)")
+        cfg_l = self._drop_cfg()
+        cfg = cfg_l
+        if cfg_l is not None and cfg_l[1] is not None:
+            # explicit keep-masks (test hook): two per pass in the reference's order (labeled pass first), joined along the batch
+            cfg_u = self._drop_cfg()
+            cfg = (cfg_l[0], torch.cat([cfg_l[1], cfg_u[1]]), torch.cat([cfg_l[2], cfg_u[2]]), 0, 0)
+        o = BackbonePairFn.apply(torch.cat([x_lab, x_unlab]), x_lab.shape[0], cfg, *self._backbone_params())
+        return (o[0], o[2], o[4], o[6]), (o[1], o[3], o[5], o[7])
 
 
 class unet_3D(_Backbone3DModule):

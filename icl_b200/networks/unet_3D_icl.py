@@ -2,6 +2,7 @@
 
 Module tree and parameter names are the reference's (so checkpoints interchange); every forward op is a
 CUDA kernel from icl_b200 (backbone: backbone3d.Backbone3DFn; heads: icl_b200.functional)."""
+import os
 from typing import Sequence
 
 import torch
@@ -223,10 +224,14 @@ class unet_3D_icl(_Backbone3DModule):
         self.uscl = InherentConsistent(**kw)
 
     def forward(self, x_lab, x_unlab=None, inference=None):
-        final_lab, center_lab, up4_lab, up3_lab = self._run(x_lab)
         if inference:
-            return final_lab
-        final_unlab, center_unlab, up4_unlab, up3_unlab = self._run(x_unlab)
+            return self._run(x_lab)[0]
+        if os.environ.get("ICL_DISABLE_PAIR") == "1" or x_lab.shape[1:] != x_unlab.shape[1:]:
+            final_lab, center_lab, up4_lab, up3_lab = self._run(x_lab)
+            final_unlab, center_unlab, up4_unlab, up3_unlab = self._run(x_unlab)
+        else:
+            # both passes share every weight and InstanceNorm is per sample: one batched pass, same values
+            (final_lab, center_lab, up4_lab, up3_lab), (final_unlab, center_unlab, up4_unlab, up3_unlab) = self._run_pair(x_lab, x_unlab)
         feats_lab = [center_lab, up4_lab, up3_lab]
         feats_unlab = [center_unlab, up4_unlab, up3_unlab]
         feat_Maps_lab, updated_Qs_lab = self.sspa(feats_lab, "labeled")

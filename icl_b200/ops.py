@@ -102,7 +102,7 @@ def conv3d_umma(pks, cins, wp, bias, cout, B, D, H, W, stats=None, split=None, o
         y0 = out if out is not None else torch.empty((B, D, H, W, cout), dtype=torch.float32, device=dev)
         y1, ld1, sp = None, 0, 0
     else:
-        y0 = torch.empty((B, D, H, W, split), dtype=torch.float32, device=dev)
+        y0 = out if out is not None else torch.empty((B, D, H, W, split), dtype=torch.float32, device=dev)
         y1 = torch.empty((B, D, H, W, cout - split), dtype=torch.float32, device=dev)
         ld1, sp = cout - split, split
     pk1 = pks[1] if len(pks) > 1 else None
@@ -216,8 +216,9 @@ def wgrad_umma_ok(cins, cout, D=2):
     return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and D % 2 == 0
 
 
-def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W):
-    """Tensor-core weight gradient from PK operands.  Returns dw [Cout, sum(cins), 3,3,3] (no bias gradient)."""
+def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W, bx=0):
+    """Tensor-core weight gradient from PK operands.  Returns dw [Cout, sum(cins), 3,3,3] (no bias gradient).
+    bx: batch size the X operands were allocated with when only their first B samples take part (0 = B)."""
     cin_total = sum(cins)
     dev = dy_pk.device
     dw = torch.empty((cout, cin_total, 3, 3, 3), dtype=torch.float32, device=dev)
@@ -228,7 +229,7 @@ def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W):
             raise RuntimeError("conv3d_wgrad_umma: unsupported shape Cin=%d Cout=%d D=%d" % (c, cout, D))
         ws = torch.empty(slots * 9 * 64 * 32, dtype=torch.float32, device=dev)
         call("icl_conv3d_wgrad_umma", P(pk), c_int(c), P(dy_pk), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(ws), c_int(B),
-             c_int(D), c_int(H), c_int(W), c_int(planes()), c_int(0), gflop=2e-9 * 27 * c * cout * B * D * H * W,
+             c_int(D), c_int(H), c_int(W), c_int(planes()), c_int(0), c_int(bx), gflop=2e-9 * 27 * c * cout * B * D * H * W,
              tag="B%d r%d %d->%d" % (B, D, c, cout))
         off += c
     return dw

@@ -54,7 +54,7 @@ int icl_repack_w_f32(const float* w, float* wp, int Cout, int Cin, int dgrad, vo
    icl_conv3d_wgrad_umma_slots() * 9*64*32 floats of per-CTA partial sums, reduced in a fixed order into dw. */
 int icl_conv3d_wgrad_umma_slots(int Cin, int Cout, int B, int D, int H, int W);
 int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, int Cout, float* dw, int Cin_total, int ci_off, float* workspace, int B,
-                          int D, int H, int W, int P, int accumulate, void* stream);
+                          int D, int H, int W, int P, int accumulate, int Bx, void* stream);
 int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, float* dw, int Cin_total, int ci_off, float* dbias, int B, int D,
                      int H, int W, void* stream);
 
