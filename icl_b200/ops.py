@@ -209,11 +209,18 @@ def conv3d_wgrad(xs, cins, dy, cout, B, D, H, W, want_bias=True):
     return dw, db
 
 
+def wgrad_ts():
+    """True: the weight gradient runs conv3d_wgrad_ts.cu (dY operand in tensor memory); ICL_WGRAD=smem selects the older
+    shared-memory-operand kernel (conv3d_wgrad_umma.cu, even depths only) for A/B measurements."""
+    return os.environ.get("ICL_WGRAD", "ts") != "smem"
+
+
 def wgrad_umma_ok(cins, cout, D=2):
-    """Shapes the tcgen05 weight-gradient kernel takes: channel multiples of 16 and an EVEN depth (it walks two planes per step)."""
+    """Shapes the tcgen05 weight-gradient kernels take: channel multiples of 16 (the shared-memory-operand kernel also needs an
+    EVEN depth, it walks two planes per step)."""
     if os.environ.get("ICL_DISABLE_UMMA") == "1" or not tensor_cores():
         return False
-    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and D % 2 == 0
+    return all(c % 16 == 0 for c in cins) and cout % 16 == 0 and (wgrad_ts() or D % 2 == 0)
 
 
 def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W, bx=0):
@@ -223,14 +230,18 @@ def conv3d_wgrad_umma(x_pks, cins, dy_pk, cout, B, D, H, W, bx=0):
     dev = dy_pk.device
     dw = torch.empty((cout, cin_total, 3, 3, 3), dtype=torch.float32, device=dev)
     off = 0
+    ts = wgrad_ts()
     for pk, c in zip(x_pks, cins):
-        slots = _lib.lib().icl_conv3d_wgrad_umma_slots(c, cout, B, D, H, W)
-        if slots <= 0:
+        if ts:
+            n = _lib.lib().icl_conv3d_wgrad_ts_workspace(c, cout, B, D, H, W)
+        else:
+            n = _lib.lib().icl_conv3d_wgrad_umma_slots(c, cout, B, D, H, W) * 9 * 64 * 32
+        if n <= 0:
             raise RuntimeError("conv3d_wgrad_umma: unsupported shape Cin=%d Cout=%d D=%d" % (c, cout, D))
-        ws = torch.empty(slots * 9 * 64 * 32, dtype=torch.float32, device=dev)
-        call("icl_conv3d_wgrad_umma", P(pk), c_int(c), P(dy_pk), c_int(cout), P(dw), c_int(cin_total), c_int(off), P(ws), c_int(B),
-             c_int(D), c_int(H), c_int(W), c_int(planes()), c_int(0), c_int(bx), gflop=2e-9 * 27 * c * cout * B * D * H * W,
-             tag="B%d r%d %d->%d" % (B, D, c, cout))
+        ws = torch.empty(n, dtype=torch.float32, device=dev)
+        call("icl_conv3d_wgrad_ts" if ts else "icl_conv3d_wgrad_umma", P(pk), c_int(c), P(dy_pk), c_int(cout), P(dw), c_int(cin_total), c_int(off),
+             P(ws), c_int(B), c_int(D), c_int(H), c_int(W), c_int(planes()), c_int(0), c_int(bx),
+             gflop=2e-9 * 27 * c * cout * B * D * H * W, tag="B%d r%d %d->%d" % (B, D, c, cout))
         off += c
     return dw
 

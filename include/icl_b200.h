@@ -55,6 +55,12 @@ int icl_repack_w_f32(const float* w, float* wp, int Cout, int Cin, int dgrad, vo
 int icl_conv3d_wgrad_umma_slots(int Cin, int Cout, int B, int D, int H, int W);
 int icl_conv3d_wgrad_umma(const void* x_pk, int Cin, const void* dy_pk, int Cout, float* dw, int Cin_total, int ci_off, float* workspace, int B,
                           int D, int H, int W, int P, int accumulate, int Bx, void* stream);
+/* tcgen05 weight gradient, dY operand in tensor memory (conv3d_wgrad_ts.cu): converter warps turn the dY PK tile into 8 (kd,kh)-shifted
+   channel-major copies in TMEM (ldmatrix.trans -> tcgen05.st), the X PK tile is the shared-memory B operand; 4 MMAs of M = 128 cover
+   the 27 taps of a 16-voxel K step.  Any depth.  `workspace`: icl_conv3d_wgrad_ts_workspace() floats of per-CTA partial sums. */
+long long icl_conv3d_wgrad_ts_workspace(int Cin, int Cout, int B, int D, int H, int W);
+int icl_conv3d_wgrad_ts(const void* x_pk, int Cin, const void* dy_pk, int Cout, float* dw, int Cin_total, int ci_off, float* workspace, int B,
+                        int D, int H, int W, int P, int accumulate, int Bx, void* stream);
 int icl_conv3d_wgrad(const float* x, int Cx, const float* dy, int Cout, float* dw, int Cin_total, int ci_off, float* dbias, int B, int D,
                      int H, int W, void* stream);
 
