@@ -175,16 +175,24 @@ conv3d_wgrad_ts_k(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         mbar_wait(afull0 + 8 * g, (uint32_t)(i & 1), 320 + g);
         tc_fence_after();
         if (elect_one()) {
+          // the short A2 MMAs first, the wide A1 MMAs last: the pipe still has ~100 clk of queued work while this warp waits for the next slot
 #pragma unroll
           for (int k = 0; k < WT_KPG; ++k) {
             const int ks = g * WT_KPG + k;
             const uint32_t ta = tmem_a0 + (uint32_t)(g * WT_SLOT_COLS + k * WT_KCOLS);
             const uint32_t acc = (i == 0 && ks == 0) ? 0u : 1u;
             const uint32_t bo = (uint32_t)(ks * 2 * WT_TW);  // 16-byte units: two lines of 8 voxels per K step
-            umma_bf16_ts(tmem_base, ta, b1 + bo, idesc1, acc);
-            if (P == 2) umma_bf16_ts(tmem_base, ta + 8, b1 + bo, idesc1, 1u);
             umma_bf16_ts(tmem_base + 3u * acs, ta + 16, b2 + bo, idesc2, acc);
             if (P == 2) umma_bf16_ts(tmem_base + 3u * acs, ta + 24, b2 + bo, idesc2, 1u);
+          }
+#pragma unroll
+          for (int k = 0; k < WT_KPG; ++k) {
+            const int ks = g * WT_KPG + k;
+            const uint32_t ta = tmem_a0 + (uint32_t)(g * WT_SLOT_COLS + k * WT_KCOLS);
+            const uint32_t acc = (i == 0 && ks == 0) ? 0u : 1u;
+            const uint32_t bo = (uint32_t)(ks * 2 * WT_TW);
+            umma_bf16_ts(tmem_base, ta, b1 + bo, idesc1, acc);
+            if (P == 2) umma_bf16_ts(tmem_base, ta + 8, b1 + bo, idesc1, 1u);
           }
           umma_commit(aempty0 + 8 * g);
           if (g == WT_GROUPS - 1) umma_commit(xempty0 + 8 * xst);
@@ -296,21 +304,41 @@ conv3d_wgrad_ts_k(const __grid_constant__ CUtensorMap mapX, const __grid_constan
   }
 }
 
-// dW[co][ci_off + ci][kd][kh][kw] (+)= sum over the CTAs of a block, in a fixed order.  One thread per (tap, co, ci) of a block;
-// consecutive threads read consecutive ci of one partial row.
+// dW[co][ci_off + ci][kd][kh][kw] (+)= sum over the CTAs of a block, in a fixed order.  A CTA of 256 threads = (256 / L) outputs x
+// L split lanes: lane l sums splits l, l + L, ... (four independent loads in flight), the L lanes are then added in order through
+// shared memory.  L = 8 for the thin layers (up to 148 splits), L = 1 for the deep ones (many blocks, few splits).
+template <int L>
 __global__ void __launch_bounds__(256) wgrad_ts_reduce_k(const float* __restrict__ partial, float* __restrict__ dw, int N, int n_ci_tiles,
                                                          int Cin_total, int ci_off, int splits, int accumulate) {
-  const int per_block = 27 * 16 * N;
+  constexpr int OUTS = 256 / L;
+  __shared__ float red[L][OUTS];
   const int ob = blockIdx.y;
   const int co_tile = ob / n_ci_tiles, ci_tile = ob % n_ci_tiles;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < per_block; i += gridDim.x * blockDim.x) {
-    const int ci = i % N, co = (i / N) % 16, tap = i / (16 * N);
-    const int kw = tap % 3, j = tap / 3;  // j = 3 * kd + kh
-    const int a = j < 8 ? kw : 3;
-    const int row = j < 8 ? j * 16 + co : 32 * (kw + 1) + co;
-    const float* src = partial + (((long long)ob * splits * 4 + a) * 128 + row) * N + ci;
-    float s = 0.f;
-    for (int sp = 0; sp < splits; ++sp) s += src[(long long)sp * 4 * 128 * N];
+  const int o = threadIdx.x % OUTS, l = threadIdx.x / OUTS;
+  const int i = blockIdx.x * OUTS + o;  // 27 * 16 * N outputs per block: a multiple of 256
+  const int ci = i % N, co = (i / N) % 16, tap = i / (16 * N);
+  const int kw = tap % 3, j = tap / 3;  // j = 3 * kd + kh
+  const int a = j < 8 ? kw : 3;
+  const int row = j < 8 ? j * 16 + co : 32 * (kw + 1) + co;
+  const long long sstride = (long long)4 * 128 * N;
+  const float* src = partial + (((long long)ob * splits * 4 + a) * 128 + row) * N + ci;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int sp = l;
+  for (; sp + 3 * L < splits; sp += 4 * L) {
+    const float v0 = src[sp * sstride], v1 = src[(sp + L) * sstride], v2 = src[(sp + 2 * L) * sstride], v3 = src[(sp + 3 * L) * sstride];
+    s0 += v0; s1 += v1; s2 += v2; s3 += v3;
+  }
+  for (; sp < splits; sp += L) s0 += src[sp * sstride];
+  float s = (s0 + s1) + (s2 + s3);
+  if (L > 1) {
+    red[l][o] = s;
+    __syncthreads();
+    if (l == 0) {
+#pragma unroll
+      for (int k = 1; k < L; ++k) s += red[k][o];
+    }
+  }
+  if (l == 0) {
     float* d = dw + ((long long)(co_tile * 16 + co) * Cin_total + ci_off + ci_tile * N + ci) * 27 + tap;
     *d = accumulate ? *d + s : s;
   }
@@ -381,7 +409,11 @@ ICL_API int icl_conv3d_wgrad_ts(const void* x_pk, int Cin, const void* dy_pk, in
   conv3d_wgrad_ts_k<<<(unsigned)(pl.blocks * pl.splits), WT_THREADS, smem, as_stream(stream)>>>(mx, my, p);
   icl_count_launch(1);
   const int per_block = 27 * 16 * pl.N;
-  wgrad_ts_reduce_k<<<dim3(cdiv(per_block, 256), pl.blocks), 256, 0, as_stream(stream)>>>(workspace, dw, pl.N, p.n_ci_tiles, Cin_total, ci_off,
-                                                                                        pl.splits, accumulate);
+  if (pl.splits >= 8)
+    wgrad_ts_reduce_k<8><<<dim3(per_block / 32, pl.blocks), 256, 0, as_stream(stream)>>>(workspace, dw, pl.N, p.n_ci_tiles, Cin_total, ci_off,
+                                                                                     pl.splits, accumulate);
+  else
+    wgrad_ts_reduce_k<1><<<dim3(per_block / 256, pl.blocks), 256, 0, as_stream(stream)>>>(workspace, dw, pl.N, p.n_ci_tiles, Cin_total, ci_off,
+                                                                                      pl.splits, accumulate);
   ICL_LAUNCHED("conv3d_wgrad_ts");
 }

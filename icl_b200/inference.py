@@ -81,6 +81,8 @@ _PINNED = {}
 def _label_to_host(label):
     """Device int64 label map -> numpy int64.  Class ids fit one byte, so 1 byte per voxel crosses PCIe (through a cached pinned
     buffer) instead of 8, and the widening back to the reference's int64 happens on the host."""
+    if not label.is_cuda:   # host-logic tests drive the window sharding with CPU stand-in networks: nothing to transfer
+        return label.numpy().astype(np.int64)
     small = label.to(torch.uint8)
     key = (small.numel(), label.device.index)
     buf = _PINNED.get(key)

@@ -43,9 +43,9 @@ class _Half:
     __slots__ = ("srcs", "w", "y", "mr", "out", "umma", "owner", "pk_bs")
 
 
-def _half_fwd(srcs, w, b, owner=None):
+def _half_fwd(srcs, w, b, owner=None, want_f32=True):
     """conv3x3x3(+bias) -> InstanceNorm -> ReLU on the virtual concat of `srcs` (list of _Act).  `owner`: the nn.Parameter `w` was
-    detached from (guards the packed-operand cache)."""
+    detached from (guards the packed-operand cache).  want_f32=False: the output is only ever read as a PK operand."""
     cins = [s.C for s in srcs]
     cout = w.shape[0]
     B, D, H, W, _ = srcs[0].shape
@@ -60,8 +60,8 @@ def _half_fwd(srcs, w, b, owner=None):
     else:
         h.y = ops.conv3d_direct([s.f32 for s in srcs], cins, ops.repack_w_f32(w, False), b, cout, B, D, H, W, stats)
     h.mr = ops.instnorm_finalize(stats, B, cout, D * H * W)
-    a, pk = ops.instnorm_relu_fwd(h.y, h.mr, ops.pk_ok(cout))
-    h.out = _Act(a, pk)
+    a, pk = ops.instnorm_relu_fwd(h.y, h.mr, ops.pk_ok(cout), want_f32=want_f32 or not ops.pk_ok(cout))
+    h.out = _Act(a, pk, tuple(h.y.shape))
     return h
 
 
@@ -117,8 +117,10 @@ def _half_bwd(h, dA, need_dx, dx_out0=None):
     return dw, db, [dx]
 
 
-def _block_fwd(srcs, p, owners=(None, None)):
-    h1 = _half_fwd(srcs, p[0], p[1], owners[0])
+def _block_fwd(srcs, p, owners=(None, None), lean=False):
+    # lean: the second convolution (forward, data gradient and weight gradient) runs on the tensor cores, so the activation
+    # between the two convolutions is never read in fp32
+    h1 = _half_fwd(srcs, p[0], p[1], owners[0], want_f32=not lean)
     h2 = _half_fwd([h1.out], p[2], p[3], owners[1])
     return (h1, h2)
 
@@ -163,12 +165,12 @@ def _forward_body(ctx, x, drop_cfg, params):
     a0 = _Act(x_, ops.pack_pk(x_) if ops.pk_ok(Cin) else None)
     enc = a0
     for i, name in enumerate(["conv1", "conv2", "conv3", "conv4"]):
-        rec[name] = _block_fwd([enc], blk[name], own[name])
+        rec[name] = _block_fwd([enc], blk[name], own[name], lean)
         out = rec[name][1].out
         pooled, idx, ppk = ops.maxpool_fwd(out.f32, ops.pk_ok(out.C), want_f32=not lean)
         rec["pool%d" % (i + 1)] = idx
         enc = _Act(pooled, ppk, (B, out.shape[1] // 2, out.shape[2] // 2, out.shape[3] // 2, out.C))
-    rec["center"] = _block_fwd([enc], blk["center"], own["center"])
+    rec["center"] = _block_fwd([enc], blk["center"], own["center"], lean)
     center = rec["center"][1].out
     if drop_cfg is not None:
         pdrop, m1, m2, s1, s2 = drop_cfg
@@ -181,7 +183,7 @@ def _forward_body(ctx, x, drop_cfg, params):
                        ("up_concat1.conv", "conv1")):
         up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
         cs = coarse.shape
-        rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name])
+        rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name], lean)
         coarse = rec[name][1].out
     up1 = coarse
     up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32

@@ -256,12 +256,14 @@ def instnorm_finalize(stats, B, C, S, eps=1e-5):
     return mr
 
 
-def instnorm_relu_fwd(y, mr, want_pk):
+def instnorm_relu_fwd(y, mr, want_pk, want_f32=True):
+    """want_f32=False (needs want_pk): only the split-bf16 operand is written — the activation between the two convolutions of a
+    UnetConv3 block is read by nothing but the next tensor-core convolution and its weight gradient."""
     B, D, H, W, C = y.shape
-    a = torch.empty_like(y)
+    a = torch.empty_like(y) if (want_f32 or not want_pk) else None
     pk = empty_pk(B, C, D, H, W, y.device) if want_pk else None
     call("icl_instnorm_relu_fwd", P(y), P(mr), P(a), P(pk), c_int(1 if planes() == 2 else 0), c_int(B), c_int(C), c_ll(D * H * W),
-         mbytes=1e-6 * y.numel() * (8 + (2 * planes() if want_pk else 0)))
+         mbytes=1e-6 * y.numel() * (4 + (4 if a is not None else 0) + (2 * planes() if want_pk else 0)))
     return a, pk
 
 

@@ -215,6 +215,9 @@ WGRAD_CASES = [
     (1, [16, 32], 16, (4, 16, 16)),  # virtual concat (up1 shape): two sources
     (1, [64], 64, (4, 12, 12)),
     (1, [128], 256, (2, 6, 6)),      # more output blocks than SMs
+    (1, [16], 16, (3, 20, 10)),      # odd depth, ragged tiles in both directions (the tensor-memory kernel walks plane by plane)
+    (2, [32], 32, (1, 16, 8)),       # a single plane: both depth neighbours are out of range
+    (1, [48], 16, (5, 8, 8)),        # Cin not a multiple of 32: three 16-channel blocks
 ]
 
 
@@ -231,9 +234,14 @@ def test_conv3d_wgrad_umma(B, cins, cout, dims, mode, tol):
         xcat = torch.cat(xs, 1).double().requires_grad_(True)
         w = torch.zeros(cout, sum(cins), 3, 3, 3, dtype=torch.float64, requires_grad=True)
         F.conv3d(xcat, w, None, padding=1).backward(dy.double())
+        if D % 2 and not ops.wgrad_ts():
+            pytest.skip("the shared-memory-operand kernel (ICL_WGRAD=smem) needs an even depth")
         dw = ops.conv3d_wgrad_umma([ops.pack_pk(cl(x)) for x in xs], cins, ops.pack_pk(cl(dy)), cout, B, D, H, W)
         torch.cuda.synchronize()
         assert_close(dw.cpu(), w.grad, tol, "wgrad umma %s" % mode)
+        dw2 = ops.conv3d_wgrad_umma([ops.pack_pk(cl(x)) for x in xs], cins, ops.pack_pk(cl(dy)), cout, B, D, H, W)
+        torch.cuda.synchronize()
+        assert torch.equal(dw, dw2), "the weight gradient must be bit-reproducible (fixed-order reduction of the per-CTA partial sums)"
     finally:
         icl_b200.set_precision("parity")
 
