@@ -32,7 +32,10 @@
 #define BW_SLOT_COLS 32  // TMEM columns per A slot: 16 (hi, 32 bf16 of k) + 16 (lo)
 
 struct BigwParams {
-  float* part;             // [splits][rows][M]
+  float* part;             // [splits][rows][M]; with `direct`: y [M][ldy] row-major (+ r0), written by the epilogue itself
+  float* pre;              // direct: optional pre-activation copy, same layout as y
+  const float* bias;       // direct: optional bias[rows]
+  int direct, act, ldy, valid_rows;
   const __nv_bfloat16* T;  // [2][kblocks*4][rows][8]
   long long t_plane;       // elements per precision plane of T
   int M, rows, kblocks, splits, stages, tmem_cols, acc_cols;
@@ -152,6 +155,34 @@ __global__ void __launch_bounds__(192, 2) bigw_gemm_k(const __grid_constant__ CU
     mbar_wait(accfull, 0, 500);
     tc_fence_after();
     const int m = mt * BW_MT + row;
+    if (p.direct) {
+      // token-major GEMM (the streamed matrix is the activation, one split): y[m][c] = act(D[m][c] + bias[c]), 64 contiguous bytes per store group
+      float* dst = p.part + (long long)m * p.ldy;
+      float* dpre = p.pre ? p.pre + (long long)m * p.ldy : nullptr;
+      for (int c0 = 0; c0 < p.valid_rows; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + lane_base + (uint32_t)c0, r);
+        if (m < p.M) {
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + ((p.bias && c0 + i < p.valid_rows) ? p.bias[c0 + i] : 0.f);
+          if (c0 + 16 <= p.valid_rows && (p.ldy & 3) == 0) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+              if (dpre) *reinterpret_cast<float4*>(dpre + c0 + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              const float4 o = p.act ? make_float4(gelu_erf(v[i]), gelu_erf(v[i + 1]), gelu_erf(v[i + 2]), gelu_erf(v[i + 3]))
+                                     : make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+              *reinterpret_cast<float4*>(dst + c0 + i) = o;
+            }
+          } else {
+            for (int i = 0; i < 16 && c0 + i < p.valid_rows; ++i) {
+              if (dpre) dpre[c0 + i] = v[i];
+              dst[c0 + i] = p.act ? gelu_erf(v[i]) : v[i];
+            }
+          }
+        }
+      }
+    } else {
     float* dst = p.part + (long long)sp * rows * p.M + m;
     for (int c0 = 0; c0 < rows; c0 += 16) {
       uint32_t r[16];
@@ -160,6 +191,7 @@ __global__ void __launch_bounds__(192, 2) bigw_gemm_k(const __grid_constant__ CU
 #pragma unroll
         for (int i = 0; i < 16; ++i) dst[(long long)(c0 + i) * p.M] = __uint_as_float(r[i]);   // a warp stores 128 contiguous bytes per row
       }
+    }
     }
   }
   tc_fence_before();
@@ -173,7 +205,7 @@ __global__ void __launch_bounds__(192, 2) bigw_gemm_k(const __grid_constant__ CU
 // S[rows][K] fp32 (row stride lds) * scale -> T[plane][K32/8][rows_pad][8] split bf16, written at row offset r0; rows in
 // [r0 + rows, rows_pad) of a chunk and columns >= K are zero-filled when `zero_pad` (the caller packs the last piece last).
 __global__ void __launch_bounds__(256) bigw_pack_k(const float* __restrict__ S, long long lds, int rows, int K, float scale, __nv_bfloat16* __restrict__ T,
-                                                   int rows_pad, int r0, int k8_total, int fill_rows) {
+                                                   int rows_pad, int r0, int k8_total, int fill_rows, long long ldk = 1) {
   // one thread per (k8 chunk, row): rows fastest, so a warp writes 512 contiguous bytes per plane
   const long long total = (long long)k8_total * fill_rows;
   const long long plane = (long long)k8_total * rows_pad * 8;
@@ -184,7 +216,7 @@ __global__ void __launch_bounds__(256) bigw_pack_k(const float* __restrict__ S, 
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       const long long k = k8 * 8 + e;
-      v[e] = (r < rows && k < K) ? S[(long long)r * lds + k] * scale : 0.f;
+      v[e] = (r < rows && k < K) ? S[(long long)r * lds + k * ldk] * scale : 0.f;
     }
     uint32_t hi[4], lo[4];
 #pragma unroll
@@ -301,6 +333,7 @@ static int bigw_run(int trans, int rows, int M, int K, const float* S, const flo
     p.part = part; p.T = T; p.t_plane = (long long)k8_total * pl.rows_pad * 8;
     p.M = M; p.rows = pl.rows_pad; p.kblocks = pl.kblocks; p.splits = pl.splits; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
     p.acc_cols = pl.acc_cols;
+    p.direct = 0; p.pre = nullptr; p.bias = nullptr; p.act = 0; p.ldy = 0; p.valid_rows = pl.rows_pad;
     const unsigned grid = (unsigned)(pl.m_tiles * pl.splits);
     if (trans) bigw_gemm_k<1><<<grid, 192, pl.smem, as_stream(stream)>>>(map, p);
     else       bigw_gemm_k<0><<<grid, 192, pl.smem, as_stream(stream)>>>(map, p);
@@ -325,6 +358,63 @@ ICL_API int icl_bigw_linear_dgrad(int rows, int N, int K, const float* dy, const
   ICL_REQUIRE(rows > 0 && N > 0 && K > 0 && K % 4 == 0, "bigw_linear_dgrad: bad shape rows=%d N=%d K=%d (K %% 4 == 0 required)", rows, N, K);
   ICL_REQUIRE(workspace != nullptr, "bigw_linear_dgrad: workspace of icl_bigw_workspace(rows, K, N) bytes required");
   return bigw_run(1, rows, K, N, dy, W, N, K, nullptr, 0, dx, nullptr, workspace, stream);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Token-major Linears on the same kernel (nn.Linear over many tokens: Swin-UNet qkv / proj / mlp, the ICL-head token
+// projections; reference networks/swinunet_icl.py:120-155, unet_3D_icl.py:277-306).  The roles swap: the STREAMED fp32
+// matrix is the activation x [tokens][K] (TMA tile 128 tokens x 32 k, split to bf16 hi/lo into TMEM as the A operand), the
+// small packed operand is the weight (<= 128 output features per pass), the reduction axis is short (one split), and the
+// epilogue writes y[token][feature] row-major with bias / GELU itself.
+//   fwd  : y[M][N]  = act(x[M][K] @ W[N][K]^T + b)      dgrad : dx[M][K] = dy[M][N] @ W[N][K]   (packs W transposed)
+ICL_API long long icl_tok_linear_workspace(int N, int K) {
+  const int np = N < 128 ? ((N + 15) / 16) * 16 : 128;
+  return 2LL * cdiv(K, BW_KB) * 4 * np * 8 * 2 + 256;
+}
+
+static int tok_linear_run(int M, int N, int K, const float* x, const float* W, long long w_lds, long long w_ldk, const float* bias, int act, float* y,
+                          float* pre, void* workspace, void* stream, const char* what) {
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(bigw_gemm_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bigw_gemm_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+    if (e != cudaSuccess) { icl_set_error("tok_linear: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+    configured = true;
+  }
+  CUtensorMap map;
+  if (make_w_map(&map, x, M, K, 0)) return -1;
+  __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(workspace);
+  for (int r0 = 0; r0 < N; r0 += 128) {
+    const int rr = N - r0 < 128 ? N - r0 : 128;
+    BigwPlan pl = bigw_plan(rr, M, K);
+    pl.splits = 1;
+    const int k8_total = pl.kblocks * 4;
+    bigw_pack_k<<<grid_for((long long)k8_total * pl.rows_pad, 256), 256, 0, as_stream(stream)>>>(W + (long long)r0 * w_lds, w_lds, rr, K, 1.f, T, pl.rows_pad, 0,
+                                                                                                   k8_total, pl.rows_pad, w_ldk);
+    icl_count_launch(1);
+    BigwParams p;
+    p.part = y + r0; p.T = T; p.t_plane = (long long)k8_total * pl.rows_pad * 8;
+    p.M = M; p.rows = pl.rows_pad; p.kblocks = pl.kblocks; p.splits = 1; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.acc_cols = pl.acc_cols;
+    p.direct = 1; p.pre = pre ? pre + r0 : nullptr; p.bias = bias ? bias + r0 : nullptr; p.act = act; p.ldy = N; p.valid_rows = rr;
+    bigw_gemm_k<0><<<(unsigned)pl.m_tiles, 192, pl.smem, as_stream(stream)>>>(map, p);
+    icl_count_launch(1);
+  }
+  return icl_check_launch(what);
+}
+
+ICL_API int icl_tok_linear_fwd(int M, int N, int K, const float* x, const float* W, const float* bias, float* y, float* pre, int act, void* workspace,
+                               void* stream) {
+  ICL_REQUIRE(M > 0 && N > 0 && K > 0 && K % 4 == 0, "tok_linear_fwd: bad shape M=%d N=%d K=%d (K %% 4 == 0 required)", M, N, K);
+  ICL_REQUIRE(workspace != nullptr, "tok_linear_fwd: workspace of icl_tok_linear_workspace(N, K) bytes required");
+  return tok_linear_run(M, N, K, x, W, K, 1, bias, act, y, pre, workspace, stream, "tok_linear_fwd");
+}
+
+ICL_API int icl_tok_linear_dgrad(int M, int N, int K, const float* dy, const float* W, float* dx, void* workspace, void* stream) {
+  ICL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 4 == 0, "tok_linear_dgrad: bad shape M=%d N=%d K=%d (N %% 4 == 0 required)", M, N, K);
+  ICL_REQUIRE(workspace != nullptr, "tok_linear_dgrad: workspace of icl_tok_linear_workspace(K, N) bytes required");
+  // output features = K (rows of W^T), reduction axis = N: element (r = k, kk = n) of the packed operand is W[n][k]
+  return tok_linear_run(M, K, N, dy, W, 1, K, nullptr, 0, dx, nullptr, workspace, stream, "tok_linear_dgrad");
 }
 
 // =====================================================================================================================

@@ -347,6 +347,18 @@ def bigw_ok(M, N, K):
     return N * K >= BIGW_MIN_NUMEL and M <= 512 and K % 4 == 0 and N % 4 == 0
 
 
+def tok_linear_ok(M, N, K):
+    """Token-major Linears the tcgen05 kernel takes (many tokens against a small weight: Swin-UNet qkv / proj / mlp, the ICL-head
+    token projections); ICL_DISABLE_TOKLIN=1 routes them back to the fp32 CUDA-core GEMM."""
+    if os.environ.get("ICL_DISABLE_TOKLIN") == "1" or not tensor_cores():
+        return False
+    return M >= 512 and N >= 16 and K >= 32 and K % 4 == 0 and N % 4 == 0
+
+
+def _tok_ws(N, K, device):
+    return torch.empty((int(_lib.lib().icl_tok_linear_workspace(N, K)),), dtype=torch.uint8, device=device)
+
+
 def _bigw_ws(rows, M, K, device):
     return torch.empty((int(_lib.lib().icl_bigw_workspace(rows, M, K)),), dtype=torch.uint8, device=device)
 
@@ -361,6 +373,9 @@ def linear_fwd(x2d, w, b, act=0, want_pre=False):
         ws = _bigw_ws(M, N, K, x2d.device)
         call("icl_bigw_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act), P(ws),
              mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
+    elif tok_linear_ok(M, N, K):
+        call("icl_tok_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act), P(_tok_ws(N, K, x2d.device)),
+             mbytes=4e-6 * (N * K + M * K + M * N * (2 if want_pre else 1)), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
     elif M <= 64 and K >= 1024 and K % 4 == 0:
         call("icl_skinny_linear_fwd", c_int(M), c_int(N), c_int(K), P(x2d), P(w), P(b), P(y), P(pre), c_int(act),
              mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
@@ -377,6 +392,11 @@ def linear_dgrad(dy2d, w):
         ws = _bigw_ws(M, K, N, dy2d.device)
         call("icl_bigw_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), P(ws), mbytes=4e-6 * (N * K + M * K + M * N),
              gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
+        return dx
+    if tok_linear_ok(M, K, N):
+        dx = torch.empty((M, K), dtype=torch.float32, device=dy2d.device)
+        call("icl_tok_linear_dgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(w), P(dx), P(_tok_ws(K, N, dy2d.device)),
+             mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
         return dx
     if M <= 64 and N >= 1024 and K % 4 == 0:
         dx = zeros((M, K), torch.float32, dy2d.device)

@@ -125,6 +125,13 @@ long long icl_bigw_workspace(int rows, int M, int K);
 int icl_bigw_linear_fwd(int rows, int N, int K, const float* x, const float* W, const float* bias, float* y, float* pre, int act, void* workspace,
                         void* stream);
 int icl_bigw_linear_dgrad(int rows, int N, int K, const float* dy, const float* W, float* dx, void* workspace, void* stream);
+/* token-major nn.Linear on the same tcgen05 kernel (roles swapped: the streamed fp32 matrix is the activation, the packed operand the
+   weight; epilogue writes y row-major with bias / GELU): Swin-UNet qkv / proj / mlp (networks/swinunet_icl.py:120-155) and the ICL-head
+   token projections (networks/unet_3D_icl.py:277-306).  workspace: icl_tok_linear_workspace(output features, reduction length) bytes. */
+long long icl_tok_linear_workspace(int N, int K);
+int icl_tok_linear_fwd(int M, int N, int K, const float* x, const float* W, const float* bias, float* y, float* pre, int act, void* workspace,
+                       void* stream);
+int icl_tok_linear_dgrad(int M, int N, int K, const float* dy, const float* W, float* dx, void* workspace, void* stream);
 int icl_colsum(const float* a, float* out, long long M, int N, int accumulate, void* stream);
 int icl_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream);
 

@@ -336,6 +336,30 @@ def test_dropout_mask_and_philox():
     assert abs(o1.max().item() - 1 / 0.7) < 1e-6
 
 
+TOK_CASES = [(3136, 288, 96, 1), (1000, 64, 64, 0), (2048, 96, 384, 0), (1024, 20, 36, 1), (4096, 384, 96, 1)]
+
+
+@pytest.mark.parametrize("M,N,K,act", TOK_CASES)
+def test_tok_linear_umma(M, N, K, act):
+    """Token-major nn.Linear on the tcgen05 kernel (Swin qkv / proj / mlp, ICL token projections): forward with bias / GELU and the
+    pre-activation copy, and the data gradient, against float64 (split-bf16 products: 1e-4)."""
+    ops = _ops()
+    assert ops.tok_linear_ok(M, N, K)
+    x = torch.randn(M, K, generator=g(11)).cuda()
+    w = (torch.randn(N, K, generator=g(12)) * 0.2).cuda()
+    b = torch.randn(N, generator=g(13)).cuda()
+    y, pre = ops.linear_fwd(x, w, b, act, want_pre=bool(act))
+    ref_pre = x.double().cpu() @ w.double().cpu().t() + b.double().cpu()
+    ref = F.gelu(ref_pre) if act else ref_pre
+    assert_close(y.cpu(), ref, 1e-4, "tok linear fwd")
+    if act:
+        assert_close(pre.cpu(), ref_pre, 1e-4, "tok linear pre-activation")
+    dy = torch.randn(M, N, generator=g(14)).cuda()
+    if ops.tok_linear_ok(M, K, N):
+        dx = ops.linear_dgrad(dy, w)
+        assert_close(dx.cpu(), dy.double().cpu() @ w.double().cpu(), 1e-4, "tok linear dgrad")
+
+
 # ------------------------------------------------------------------------------------------ GEMM family / heads
 @pytest.mark.parametrize("M,N,K", [(7, 33, 19), (130, 70, 65), (16, 2048, 1024), (3, 1030, 1100), (40, 1536, 1536), (32, 1728, 1728),
                                    (16, 1100, 2052), (64, 1027, 1028), (16, 4100, 2052), (24, 4608, 1028), (5, 4097, 260), (16, 8200, 2052),
