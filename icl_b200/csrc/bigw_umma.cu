@@ -228,13 +228,15 @@ __global__ void __launch_bounds__(256) bigw_pack_k(const float* __restrict__ S, 
 }
 
 // y[r][m] = act(sum_s part[s][r][m] + bias[m]); pre (optional) = the pre-activation value
+// t_ld > 0: transposed output y[m * t_ld + r] (the token-major weight gradient: partials are [feature r][output row m])
 __global__ void __launch_bounds__(256) bigw_finish_k(const float* __restrict__ part, int splits, int rows_pad, int rows, int M, const float* __restrict__ bias,
-                                                     int act, float* __restrict__ y, float* __restrict__ pre) {
+                                                     int act, float* __restrict__ y, float* __restrict__ pre, int t_ld = 0) {
   const long long total = (long long)rows * M;
   const long long sstride = (long long)rows_pad * M;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     float a = part[i];
     for (int s = 1; s < splits; ++s) a += part[i + s * sstride];
+    if (t_ld > 0) { y[(i % M) * t_ld + i / M] = a; continue; }
     if (bias) a += bias[i % M];
     if (pre) pre[i] = a;
     y[i] = act ? gelu_erf(a) : a;
@@ -415,6 +417,57 @@ ICL_API int icl_tok_linear_dgrad(int M, int N, int K, const float* dy, const flo
   ICL_REQUIRE(workspace != nullptr, "tok_linear_dgrad: workspace of icl_tok_linear_workspace(K, N) bytes required");
   // output features = K (rows of W^T), reduction axis = N: element (r = k, kk = n) of the packed operand is W[n][k]
   return tok_linear_run(M, K, N, dy, W, 1, K, nullptr, 0, dx, nullptr, workspace, stream, "tok_linear_dgrad");
+}
+
+//   wgrad: dW[N][K] = dy[M][N]^T @ x[M][K]: the streamed matrix is dy in [reduction = token][output row n] order (the TRANS tile path),
+//          the packed operand x^T (<= 128 weight columns per pass), the token axis is cut into splits whose partials are summed in a
+//          fixed order and written transposed into dW.
+ICL_API long long icl_tok_linear_wgrad_workspace(int M, int N, int K) {
+  const int kp = K < 128 ? ((K + 15) / 16) * 16 : 128;
+  const long long t = 2LL * cdiv(M, BW_KB) * 4 * kp * 8 * 2;
+  return ((t + 255) / 256) * 256 + 128LL * kp * N * 4;
+}
+
+ICL_API int icl_tok_linear_wgrad(int M, int N, int K, const float* dy, const float* x, float* dW, void* workspace, void* stream) {
+  ICL_REQUIRE(M > 0 && N > 0 && K > 0 && N % 4 == 0, "tok_linear_wgrad: bad shape M=%d N=%d K=%d (N %% 4 == 0 required)", M, N, K);
+  ICL_REQUIRE(workspace != nullptr, "tok_linear_wgrad: workspace of icl_tok_linear_wgrad_workspace(M, N, K) bytes required");
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(bigw_gemm_k<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(bigw_gemm_k<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(112 * 1024));
+    if (e != cudaSuccess) { icl_set_error("tok_linear_wgrad: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return -2; }
+    configured = true;
+  }
+  CUtensorMap map;
+  if (make_w_map(&map, dy, M, N, 1)) return -1;
+  for (int r0 = 0; r0 < K; r0 += 128) {
+    const int rr = K - r0 < 128 ? K - r0 : 128;
+    BigwPlan pl = bigw_plan(rr, N, M);
+    // few output tiles, a long reduction: cut the token axis until the CTAs fill the chip (at most 128 partial slabs)
+    int splits = 296 / pl.m_tiles;
+    if (splits > 128) splits = 128;
+    if (splits > pl.kblocks) splits = pl.kblocks;
+    if (splits < 1) splits = 1;
+    pl.splits = splits;
+    __nv_bfloat16* T = reinterpret_cast<__nv_bfloat16*>(workspace);
+    const long long t_bytes = 2LL * pl.kblocks * 4 * pl.rows_pad * 8 * 2;
+    float* part = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((t_bytes + 255) / 256) * 256);
+    const int k8_total = pl.kblocks * 4;
+    // packed operand row r = weight column r0 + r, reduction index = token: x[token][r0 + r]
+    bigw_pack_k<<<grid_for((long long)k8_total * pl.rows_pad, 256), 256, 0, as_stream(stream)>>>(x + r0, 1, rr, M, 1.f, T, pl.rows_pad, 0, k8_total,
+                                                                                                   pl.rows_pad, (long long)K);
+    icl_count_launch(1);
+    BigwParams p;
+    p.part = part; p.T = T; p.t_plane = (long long)k8_total * pl.rows_pad * 8;
+    p.M = N; p.rows = pl.rows_pad; p.kblocks = pl.kblocks; p.splits = pl.splits; p.stages = pl.stages; p.tmem_cols = pl.tmem_cols;
+    p.acc_cols = pl.acc_cols;
+    p.direct = 0; p.pre = nullptr; p.bias = nullptr; p.act = 0; p.ldy = 0; p.valid_rows = pl.rows_pad;
+    bigw_gemm_k<1><<<(unsigned)(pl.m_tiles * pl.splits), 192, pl.smem, as_stream(stream)>>>(map, p);
+    icl_count_launch(1);
+    bigw_finish_k<<<grid_for((long long)rr * N, 256), 256, 0, as_stream(stream)>>>(part, pl.splits, pl.rows_pad, rr, N, nullptr, 0, dW + r0, nullptr, K);
+    icl_count_launch(1);
+  }
+  return icl_check_launch("tok_linear_wgrad");
 }
 
 // =====================================================================================================================

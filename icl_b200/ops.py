@@ -414,7 +414,13 @@ def linear_wgrad(dy2d, x2d, want_bias=True):
     K = x2d.shape[1]
     dW = torch.empty((N, K), dtype=torch.float32, device=dy2d.device)
     db = torch.empty((N,), dtype=torch.float32, device=dy2d.device) if want_bias else None
-    if M <= 64 and N * K >= (1 << 20):
+    if tok_linear_ok(M, N, K) and M >= 2048 and K % 4 == 0:
+        ws = torch.empty((int(_lib.lib().icl_tok_linear_wgrad_workspace(M, N, K)),), dtype=torch.uint8, device=dy2d.device)
+        call("icl_tok_linear_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(ws), mbytes=4e-6 * (N * K + M * K + M * N),
+             gflop=2e-9 * M * N * K, tag="%dx%dx%d" % (M, N, K))
+        if want_bias:
+            call("icl_colsum", P(dy2d), P(db), c_ll(M), c_int(N), c_int(0), tag="%dx%d" % (M, N))
+    elif M <= 64 and N * K >= (1 << 20):
         call("icl_outer_wgrad", c_int(M), c_int(N), c_int(K), P(dy2d), P(x2d), P(dW), P(db), c_int(0),
              mbytes=4e-6 * (N * K + M * K + M * N), gflop=2e-9 * M * N * K)
     else:

@@ -132,6 +132,8 @@ long long icl_tok_linear_workspace(int N, int K);
 int icl_tok_linear_fwd(int M, int N, int K, const float* x, const float* W, const float* bias, float* y, float* pre, int act, void* workspace,
                        void* stream);
 int icl_tok_linear_dgrad(int M, int N, int K, const float* dy, const float* W, float* dx, void* workspace, void* stream);
+long long icl_tok_linear_wgrad_workspace(int M, int N, int K);
+int icl_tok_linear_wgrad(int M, int N, int K, const float* dy, const float* x, float* dW, void* workspace, void* stream);
 int icl_colsum(const float* a, float* out, long long M, int N, int accumulate, void* stream);
 int icl_gelu_bwd(const float* dy, const float* pre, float* dx, long long n, void* stream);
 

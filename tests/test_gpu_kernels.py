@@ -358,6 +358,10 @@ def test_tok_linear_umma(M, N, K, act):
     if ops.tok_linear_ok(M, K, N):
         dx = ops.linear_dgrad(dy, w)
         assert_close(dx.cpu(), dy.double().cpu() @ w.double().cpu(), 1e-4, "tok linear dgrad")
+    if M >= 2048:
+        dW, db = ops.linear_wgrad(dy, x, True)
+        assert_close(dW.cpu(), dy.double().cpu().t() @ x.double().cpu(), 1e-4, "tok linear wgrad")
+        assert_close(db.cpu(), dy.double().cpu().sum(0), 1e-4, "tok linear bias grad")
 
 
 # ------------------------------------------------------------------------------------------ GEMM family / heads

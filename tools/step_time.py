@@ -50,6 +50,23 @@ def run(name, net, x, y, n_lab, size, iters=5):
         torch.cuda.synchronize()
         ts.append(e0.elapsed_time(e1))
     ms = sorted(ts)[len(ts) // 2]
+    if "--kernels" in sys.argv:   # per-kernel device time of the (replayed) step from CUPTI records
+        import collections
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+        agg = collections.defaultdict(lambda: [0.0, 0])
+        for ev in prof.events():
+            if ev.device_type == torch.autograd.DeviceType.CUDA:
+                n = ev.name.split("(")[0].replace("void ", "")
+                agg[n][0] += ev.device_time
+                agg[n][1] += 1
+        tot = sum(v[0] for v in agg.values())
+        print("# %s: %d kernels, %.2f ms kernel time per step" % (name, sum(v[1] for v in agg.values()) // 2, tot / 2e3))
+        for n, (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])[:25]:
+            print("  %-60s %7.1f x %9.1f us/step %5.1f%%  %8.2f us/launch" % (n[:60], c / 2, us / 2, 100 * us / tot, us / c))
     print("%s: %.1f ms/step (fwd + 5 losses + bwd, eager), %.0f slices/s, loss %.4f" % (name, ms, 1e3 * x.shape[0] / ms, loss.item()), flush=True)
 
 
