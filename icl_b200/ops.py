@@ -352,7 +352,10 @@ def tok_linear_ok(M, N, K):
     token projections); ICL_DISABLE_TOKLIN=1 routes them back to the fp32 CUDA-core GEMM."""
     if os.environ.get("ICL_DISABLE_TOKLIN") == "1" or not tensor_cores():
         return False
-    return M >= 512 and N >= 16 and K >= 32 and K % 4 == 0 and N % 4 == 0
+    # below ~0.8 GFLOP the pack + GEMM (+ finish) launches cost more than the fp32 CUDA-core GEMM they replace (measured on the ICL-head
+    # token projections, 27 648 x 64 x 64: the replayed step got 0.3 ms slower); ICL_TOKLIN_MIN_FLOP overrides (tests use 0)
+    min_flop = float(os.environ.get("ICL_TOKLIN_MIN_FLOP", "0.8e9"))
+    return M >= 512 and N >= 16 and K >= 32 and K % 4 == 0 and N % 4 == 0 and 2.0 * M * N * K >= min_flop
 
 
 def _tok_ws(N, K, device):

@@ -44,7 +44,7 @@ def main():
     agg = collections.defaultdict(lambda: [0.0, 0])
     for ev in prof.events():
         if ev.device_type == torch.autograd.DeviceType.CUDA:
-            n = ev.name.split("(")[0].replace("void ", "")
+            n = ev.name.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "")
             agg[n][0] += ev.device_time if hasattr(ev, "device_time") else ev.cuda_time
             agg[n][1] += 1
     tot = sum(v[0] for v in agg.values())

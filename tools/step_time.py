@@ -60,7 +60,7 @@ def run(name, net, x, y, n_lab, size, iters=5):
         agg = collections.defaultdict(lambda: [0.0, 0])
         for ev in prof.events():
             if ev.device_type == torch.autograd.DeviceType.CUDA:
-                n = ev.name.split("(")[0].replace("void ", "")
+                n = ev.name.replace("(anonymous namespace)::", "").split("(")[0].replace("void ", "")
                 agg[n][0] += ev.device_time
                 agg[n][1] += 1
         tot = sum(v[0] for v in agg.values())
