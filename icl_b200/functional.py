@@ -171,7 +171,8 @@ class WindowAttnFn(torch.autograd.Function):
         B, H, W, C, nH, ws, shift = ctx.dims
         dqkv = torch.empty_like(q_)
         dtable = torch.zeros_like(t_)
-        call("icl_window_attn_bwd", P(q_), P(t_), P(_c(dout)), P(dqkv), P(dtable), c_int(B), c_int(H), c_int(W), c_int(C), c_int(nH),
+        dout_c = _c(dout)   # keep the contiguous copy alive across the launch
+        call("icl_window_attn_bwd", P(q_), P(t_), P(dout_c), P(dqkv), P(dtable), c_int(B), c_int(H), c_int(W), c_int(C), c_int(nH),
              c_int(ws), c_int(shift))
         return dqkv, dtable, None, None, None, None, None
 
