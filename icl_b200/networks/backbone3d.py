@@ -144,21 +144,26 @@ def _add(a, b):
     return a
 
 
-def _forward_body(ctx, x, drop_cfg, params):
-    """Forward of the whole backbone on the batch x; records everything backward needs on ctx.  Returns the NDHWC tensors
-    (final logits, center after dropout1, up4, up3)."""
-    ctx.set_materialize_grads(False)
-    p = [t.detach() for t in params]
-    blk = {name: p[4 * i:4 * i + 4] for i, name in enumerate(PARAM_BLOCKS)}
-    own = {name: (params[4 * i], params[4 * i + 2]) for i, name in enumerate(PARAM_BLOCKS)}   # weight Parameters of conv1 / conv2
-    wf, bf = p[36], p[37]
+LOW_BLOCKS = PARAM_BLOCKS[:7]    # encoder, center, up_concat4, up_concat3: everything the ICL heads read
+TOP_BLOCKS = PARAM_BLOCKS[7:]    # up_concat2, up_concat1 (+ final): 48^3 / 96^3 levels, never seen by the heads
+N_LOW = 4 * len(LOW_BLOCKS)
+
+
+def _forward_low(st, x, drop_cfg, params_low, top_weights):
+    """Encoder, center (+ dropout1), up_concat4, up_concat3 on the batch x; records what backward and _forward_top need on `st`
+    (an autograd ctx or a _PairState).  `top_weights`: the conv weights of up_concat2 / up_concat1 (only their shapes are read: the
+    activation formats are chosen for the whole network).  Returns the NDHWC tensors (center after dropout1, up4, up3)."""
+    p = [t.detach() for t in params_low]
+    st.blk = {name: p[4 * i:4 * i + 4] for i, name in enumerate(LOW_BLOCKS)}
+    st.own = {name: (params_low[4 * i], params_low[4 * i + 2]) for i, name in enumerate(LOW_BLOCKS)}   # weight Parameters of conv1 / conv2
+    blk, own = st.blk, st.own
     x_ = ops.to_ndhwc(x.detach())
     B, D, H, W, Cin = x_.shape
     # every conv from the second one on runs on the tensor cores when all channel counts are multiples of 16:
     # pooled / upsampled tensors are then only ever read as PK operands and their fp32 copies are not written
     # (the tensor-core weight gradient needs an even depth at every level: with D % 32 != 0 the `center` level has an odd
     # depth, its weight gradient runs on the CUDA-core kernel and reads the fp32 copies, so they must exist)
-    lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2:36:2]) and ops.wgrad_umma_ok([16], 16, D // 16)
+    lean = all(ops.umma_ok([t.shape[1]], t.shape[0]) for t in p[2::2] + list(top_weights)) and ops.wgrad_umma_ok([16], 16, D // 16)
     if D % 16 or H % 16 or W % 16:
         raise RuntimeError("unet_3D backbone: spatial size must be a multiple of 16, got %s" % ((D, H, W),))
     rec = {}
@@ -179,17 +184,37 @@ def _forward_body(ctx, x, drop_cfg, params):
     else:
         center_d = center
     coarse = center_d
-    for name, skip in (("up_concat4.conv", "conv4"), ("up_concat3.conv", "conv3"), ("up_concat2.conv", "conv2"),
-                       ("up_concat1.conv", "conv1")):
-        up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
-        cs = coarse.shape
-        rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name], lean)
-        coarse = rec[name][1].out
+    for name, skip in (("up_concat4.conv", "conv4"), ("up_concat3.conv", "conv3")):
+        coarse = _up_fwd(rec, name, skip, coarse, blk, own, lean)
+    st.rec, st.drop_cfg, st.lean = rec, drop_cfg, lean
+    st.needs_x = x.requires_grad
+    return (center_d.f32, rec["up_concat4.conv"][1].out.f32, rec["up_concat3.conv"][1].out.f32)
+
+
+def _up_fwd(rec, name, skip, coarse, blk, own, lean):
+    up_f32, up_pk = ops.upsample2x_fwd(coarse.f32, ops.pk_ok(coarse.C), want_f32=not lean)
+    cs = coarse.shape
+    rec[name] = _block_fwd([rec[skip][1].out, _Act(up_f32, up_pk, (cs[0], 2 * cs[1], 2 * cs[2], 2 * cs[3], cs[4]))], blk[name], own[name], lean)
+    return rec[name][1].out
+
+
+def _forward_top(st, params_top):
+    """up_concat2, up_concat1, dropout2 and the 1x1x1 `final` conv on top of what _forward_low recorded.  Returns the NDHWC logits."""
+    p = [t.detach() for t in params_top]
+    for i, name in enumerate(TOP_BLOCKS):
+        st.blk[name] = p[4 * i:4 * i + 4]
+        st.own[name] = (params_top[4 * i], params_top[4 * i + 2])
+    wf, bf = p[8], p[9]
+    rec, drop_cfg = st.rec, st.drop_cfg
+    coarse = rec["up_concat3.conv"][1].out
+    for name, skip in (("up_concat2.conv", "conv2"), ("up_concat1.conv", "conv1")):
+        coarse = _up_fwd(rec, name, skip, coarse, st.blk, st.own, st.lean)
     up1 = coarse
-    up1d = ops.dropout(up1.f32, pdrop, m2, s2) if drop_cfg is not None else up1.f32
+    up1d = ops.dropout(up1.f32, drop_cfg[0], drop_cfg[2], drop_cfg[4]) if drop_cfg is not None else up1.f32
+    B, D, H, W, _ = up1.shape
     K = wf.shape[0]
     rows = B * D * H * W
-    final = torch.empty((B, D, H, W, K), dtype=torch.float32, device=x_.device)
+    final = torch.empty((B, D, H, W, K), dtype=torch.float32, device=up1d.device)
     wf2 = wf.reshape(K, -1)
     if wf2.shape[1] == 16 and K <= 16:
         ops.call("icl_head1x1_fwd", ops.P(up1d), ops.P(wf2), ops.P(bf), ops.P(final), ops.c_ll(rows), ops.c_int(16), ops.c_int(K),
@@ -197,10 +222,16 @@ def _forward_body(ctx, x, drop_cfg, params):
     else:
         ops.sgemm(rows, K, wf2.shape[1], up1d, wf2.shape[1], 1, wf2, 1, wf2.shape[1], final, K, 1, bias=bf, bias_mode=1)
     rec["up1d"] = up1d
-    ctx.rec, ctx.blk, ctx.wf, ctx.drop_cfg = rec, blk, wf2, drop_cfg
-    ctx.needs_x = x.requires_grad
-    return (final, center_d.f32, rec["up_concat4.conv"][1].out.f32, rec["up_concat3.conv"][1].out.f32)
+    st.wf = wf2
+    return final
 
+
+def _forward_body(ctx, x, drop_cfg, params):
+    """Forward of the whole backbone on the batch x; records everything backward needs on ctx.  Returns the NDHWC tensors
+    (final logits, center after dropout1, up4, up3)."""
+    ctx.set_materialize_grads(False)
+    low = _forward_low(ctx, x, drop_cfg, params[:N_LOW], params[N_LOW:N_LOW + 8:2])
+    return (_forward_top(ctx, params[N_LOW:]),) + low
 
 
 class Backbone3DFn(torch.autograd.Function):
@@ -310,6 +341,130 @@ def _head_bwd(gf, up1d, wf2):
     return d_up1d, [dwf.reshape(K, C1, 1, 1, 1), dbf]
 
 
+def _assemble(shape_full, parts, nl, dev):
+    """Full-batch gradient from row-range pieces [(row0, row1, tensor)]; rows nobody covers are zero.  None if no piece.
+    Pieces are cut at the labeled / unlabeled boundary, so every piece covers exactly one of the two segments."""
+    cut = []
+    for a, b_, t in parts:
+        if t is None or a == b_:
+            continue
+        if a < nl < b_:
+            cut += [(a, nl, t[:nl - a]), (nl, b_, t[nl - a:])]
+        else:
+            cut.append((a, b_, t))
+    if not cut:
+        return None
+    out = torch.empty(shape_full, dtype=torch.float32, device=dev)
+    for seg in ((0, nl), (nl, shape_full[0])):
+        if seg[0] == seg[1]:
+            continue
+        mine = [t for a, b_, t in cut if (a, b_) == seg]
+        if not mine:
+            out[seg[0]:seg[1]].zero_()
+            continue
+        out[seg[0]:seg[1]].copy_(mine[0])
+        for t in mine[1:]:
+            ops.axpby(t.contiguous(), out[seg[0]:seg[1]], 1.0, 1.0)
+    return out
+
+
+_nd = lambda g: None if g is None else ops.to_ndhwc(g)
+
+
+def _pair_bwd_top(st, nl, B, gfl, gfu):
+    """Backward of final, dropout2, up_concat1, up_concat2 on the samples whose logits carry a gradient (the labeled prefix unless
+    final_unlab received one).  Returns (parameter gradients {block: [...]}, nh, skip-gradient buffers, d_up3 of the first nh samples)."""
+    rec, wf2, drop_cfg = st.rec, st.wf, st.drop_cfg
+    dev = wf2.device
+    grads = {}
+    gfl, gfu = _nd(gfl), _nd(gfu)
+    nh = 0
+    if gfu is not None:
+        nh = B
+        gf = _assemble((B,) + tuple(gfu.shape[1:]), [(0, nl, gfl), (nl, B, gfu)], nl, dev)
+    elif gfl is not None:
+        nh, gf = nl, gfl
+    d_skip = {"conv1": None, "conv2": None}   # full-batch buffers whose first nh samples hold the skip gradients
+    d_up3_head = None
+    if nh:
+        d_up1d, grads["final"] = _head_bwd(gf, rec["up1d"][:nh], wf2)
+        if drop_cfg is not None:
+            m2 = None if drop_cfg[2] is None else drop_cfg[2][:nh]
+            d_up = ops.dropout(d_up1d, drop_cfg[0], m2, drop_cfg[4])
+        else:
+            d_up = d_up1d
+        for name, skip, below in (("up_concat1.conv", "conv1", "up_concat2.conv"), ("up_concat2.conv", "conv2", "up_concat3.conv")):
+            full = torch.empty(rec[skip][1].out.shape, dtype=torch.float32, device=dev)
+            pg, dxs = _block_bwd(rec[name], d_up, True, n=nh, dx_out0=full[:nh])
+            grads[name] = pg
+            d_skip[skip] = full
+            cs = rec[below][1].out.shape
+            d_up = torch.empty((nh,) + tuple(cs[1:]), dtype=torch.float32, device=dev)
+            ops.upsample2x_bwd(dxs[1], 0, cs[4], d_up, False)
+        d_up3_head = d_up
+    return grads, nh, d_skip, d_up3_head
+
+
+def _pair_bwd_low(st, nl, B, nh, d_skip, d_up3_head, gcl, gcu, g4l, g4u, g3l, g3u):
+    """Backward of the layers both branches reach (up_concat3/4, center, encoder) on the whole batch, with the per-branch gradients
+    assembled per row range.  Returns (parameter gradients {block: [...]}, dx or None)."""
+    rec, drop_cfg = st.rec, st.drop_cfg
+    dev = rec["center"][1].y.device
+    grads = {}
+
+    def up_block_bwd(name, dA, coarse_shape):
+        pg, dxs = _block_bwd(rec[name], dA, True)
+        grads[name] = pg
+        dcoarse = torch.empty(coarse_shape, dtype=torch.float32, device=dev)
+        ops.upsample2x_bwd(dxs[1], 0, coarse_shape[4], dcoarse, False)
+        return dxs[0], dcoarse
+
+    s3, s4, sc = rec["up_concat3.conv"][1].out.shape, rec["up_concat4.conv"][1].out.shape, rec["center"][1].out.shape
+    d_c3 = d_c4 = None
+    d_up3 = _assemble(tuple(s3), [(0, nl, _nd(g3l)), (nl, B, _nd(g3u)), (0, nh, d_up3_head)], nl, dev)
+    d_up4_in = d_cd_in = None
+    if d_up3 is not None:
+        d_c3, d_up4_in = up_block_bwd("up_concat3.conv", d_up3, tuple(s4))
+    d_up4 = _assemble(tuple(s4), [(0, nl, _nd(g4l)), (nl, B, _nd(g4u)), (0, B, d_up4_in)], nl, dev)
+    if d_up4 is not None:
+        d_c4, d_cd_in = up_block_bwd("up_concat4.conv", d_up4, tuple(sc))
+    d_cd = _assemble(tuple(sc), [(0, nl, _nd(gcl)), (nl, B, _nd(gcu)), (0, B, d_cd_in)], nl, dev)
+    dx_in = None
+    if d_cd is not None:
+        d_center = ops.dropout(d_cd, drop_cfg[0], drop_cfg[1], drop_cfg[3]) if drop_cfg is not None else d_cd
+        pg, dxs = _block_bwd(rec["center"], d_center, True)
+        grads["center"] = pg
+        d_pool = dxs[0]
+        d_full = {"conv4": d_c4, "conv3": d_c3, "conv2": d_skip["conv2"], "conv1": d_skip["conv1"]}
+        for i, name in reversed(list(enumerate(["conv1", "conv2", "conv3", "conv4"]))):
+            idx = rec["pool%d" % (i + 1)]
+            dc = d_full[name]
+            if dc is None:
+                dc = torch.empty(rec[name][1].out.shape, dtype=torch.float32, device=dev)
+                ops.maxpool_bwd(d_pool, idx, dc, False)
+            elif name in ("conv1", "conv2") and nh < B:
+                # skip gradients exist for the first nh samples only: accumulate there, plain write for the rest
+                ops.maxpool_bwd(d_pool[:nh], idx[:nh], dc[:nh], True)
+                ops.maxpool_bwd(d_pool[nh:], idx[nh:], dc[nh:], False)
+            else:
+                ops.maxpool_bwd(d_pool, idx, dc, True)
+            need_dx = (i > 0) or st.needs_x
+            pg, dxs = _block_bwd(rec[name], dc, need_dx)
+            grads[name] = pg
+            d_pool = dxs[0] if dxs is not None else None
+        dx_in = ops.to_ncdhw_view(d_pool) if (st.needs_x and d_pool is not None) else None
+    return grads, dx_in
+
+
+def _flat(grads, names, with_final=False):
+    out = []
+    for name in names:
+        out += grads.get(name, [None, None, None, None])
+    if with_final:
+        out += grads.get("final", [None, None])
+    return out
+
+
 class BackbonePairFn(torch.autograd.Function):
     """The labeled and the unlabeled pass of unet_3D_icl.forward (unet_3D_icl.py:100-139) as ONE batched backbone pass:
     (x = cat([x_lab, x_unlab]), n_lab, drop_cfg, *38 params) ->
@@ -332,109 +487,70 @@ class BackbonePairFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, gfl, gfu, gcl, gcu, g4l, g4u, g3l, g3u):
-        rec, wf2, drop_cfg, nl, B = ctx.rec, ctx.wf, ctx.drop_cfg, ctx.n_lab, ctx.B
-        grads = {}
-        nd = lambda g: None if g is None else ops.to_ndhwc(g)
-        dev = wf2.device
-
-        def assemble(shape_full, parts):
-            """Full-batch gradient from row-range pieces [(row0, row1, tensor)]; rows nobody covers are zero.  None if no piece.
-            Pieces are cut at the labeled / unlabeled boundary, so every piece covers exactly one of the two segments."""
-            cut = []
-            for a, b_, t in parts:
-                if t is None or a == b_:
-                    continue
-                if a < nl < b_:
-                    cut += [(a, nl, t[:nl - a]), (nl, b_, t[nl - a:])]
-                else:
-                    cut.append((a, b_, t))
-            if not cut:
-                return None
-            out = torch.empty(shape_full, dtype=torch.float32, device=dev)
-            for seg in ((0, nl), (nl, shape_full[0])):
-                if seg[0] == seg[1]:
-                    continue
-                mine = [t for a, b_, t in cut if (a, b_) == seg]
-                if not mine:
-                    out[seg[0]:seg[1]].zero_()
-                    continue
-                out[seg[0]:seg[1]].copy_(mine[0])
-                for t in mine[1:]:
-                    ops.axpby(t.contiguous(), out[seg[0]:seg[1]], 1.0, 1.0)
-            return out
-
-        # ---- head section: final, dropout2, up_concat1, up_concat2 on the samples whose logits carry a gradient
-        gfl, gfu = nd(gfl), nd(gfu)
-        nh = 0
-        if gfu is not None:
-            nh = B
-            gf = assemble((B,) + tuple(gfu.shape[1:]), [(0, nl, gfl), (nl, B, gfu)])
-        elif gfl is not None:
-            nh, gf = nl, gfl
-        d_skip = {"conv1": None, "conv2": None}   # full-batch buffers whose first nh samples hold the skip gradients
-        d_up3_head = None
-        if nh:
-            d_up1d, grads["final"] = _head_bwd(gf, rec["up1d"][:nh], wf2)
-            if drop_cfg is not None:
-                m2 = None if drop_cfg[2] is None else drop_cfg[2][:nh]
-                d_up = ops.dropout(d_up1d, drop_cfg[0], m2, drop_cfg[4])
-            else:
-                d_up = d_up1d
-            for name, skip, below in (("up_concat1.conv", "conv1", "up_concat2.conv"), ("up_concat2.conv", "conv2", "up_concat3.conv")):
-                full = torch.empty(rec[skip][1].out.shape, dtype=torch.float32, device=dev)
-                pg, dxs = _block_bwd(rec[name], d_up, True, n=nh, dx_out0=full[:nh])
-                grads[name] = pg
-                d_skip[skip] = full
-                cs = rec[below][1].out.shape
-                d_up = torch.empty((nh,) + tuple(cs[1:]), dtype=torch.float32, device=dev)
-                ops.upsample2x_bwd(dxs[1], 0, cs[4], d_up, False)
-            d_up3_head = d_up
-
-        # ---- shared section on the whole batch
-        def up_block_bwd(name, dA, coarse_shape):
-            pg, dxs = _block_bwd(rec[name], dA, True)
-            grads[name] = pg
-            dcoarse = torch.empty(coarse_shape, dtype=torch.float32, device=dev)
-            ops.upsample2x_bwd(dxs[1], 0, coarse_shape[4], dcoarse, False)
-            return dxs[0], dcoarse
-
-        s3, s4, sc = rec["up_concat3.conv"][1].out.shape, rec["up_concat4.conv"][1].out.shape, rec["center"][1].out.shape
-        d_c3 = d_c4 = None
-        d_up3 = assemble(tuple(s3), [(0, nl, nd(g3l)), (nl, B, nd(g3u)), (0, nh, d_up3_head)])
-        d_up4_in = d_cd_in = None
-        if d_up3 is not None:
-            d_c3, d_up4_in = up_block_bwd("up_concat3.conv", d_up3, tuple(s4))
-        d_up4 = assemble(tuple(s4), [(0, nl, nd(g4l)), (nl, B, nd(g4u)), (0, B, d_up4_in)])
-        if d_up4 is not None:
-            d_c4, d_cd_in = up_block_bwd("up_concat4.conv", d_up4, tuple(sc))
-        d_cd = assemble(tuple(sc), [(0, nl, nd(gcl)), (nl, B, nd(gcu)), (0, B, d_cd_in)])
-        dx_in = None
-        if d_cd is not None:
-            d_center = ops.dropout(d_cd, drop_cfg[0], drop_cfg[1], drop_cfg[3]) if drop_cfg is not None else d_cd
-            pg, dxs = _block_bwd(rec["center"], d_center, True)
-            grads["center"] = pg
-            d_pool = dxs[0]
-            d_full = {"conv4": d_c4, "conv3": d_c3, "conv2": d_skip["conv2"], "conv1": d_skip["conv1"]}
-            for i, name in reversed(list(enumerate(["conv1", "conv2", "conv3", "conv4"]))):
-                idx = rec["pool%d" % (i + 1)]
-                dc = d_full[name]
-                if dc is None:
-                    dc = torch.empty(rec[name][1].out.shape, dtype=torch.float32, device=dev)
-                    ops.maxpool_bwd(d_pool, idx, dc, False)
-                elif name in ("conv1", "conv2") and nh < B:
-                    # skip gradients exist for the first nh samples only: accumulate there, plain write for the rest
-                    ops.maxpool_bwd(d_pool[:nh], idx[:nh], dc[:nh], True)
-                    ops.maxpool_bwd(d_pool[nh:], idx[nh:], dc[nh:], False)
-                else:
-                    ops.maxpool_bwd(d_pool, idx, dc, True)
-                need_dx = (i > 0) or ctx.needs_x
-                pg, dxs = _block_bwd(rec[name], dc, need_dx)
-                grads[name] = pg
-                d_pool = dxs[0] if dxs is not None else None
-            dx_in = ops.to_ncdhw_view(d_pool) if (ctx.needs_x and d_pool is not None) else None
-        out = []
-        for name in PARAM_BLOCKS:
-            out += grads.get(name, [None, None, None, None])
-        out += grads.get("final", [None, None])
+        nl, B = ctx.n_lab, ctx.B
+        gt, nh, d_skip, d_up3_head = _pair_bwd_top(ctx, nl, B, gfl, gfu)
+        gl, dx_in = _pair_bwd_low(ctx, nl, B, nh, d_skip, d_up3_head, gcl, gcu, g4l, g4u, g3l, g3u)
+        gl.update(gt)
         ctx.rec = None
-        return (dx_in, None, None) + tuple(out)
+        return (dx_in, None, None) + tuple(_flat(gl, PARAM_BLOCKS, with_final=True))
+
+
+class _PairState:
+    """What BackbonePairLowFn and BackbonePairTopFn share: the recorded activations of the forward pass and, during backward, the
+    gradients the top section hands down (skip connections of conv1 / conv2, d up3 of the samples that went through it)."""
+
+    def __init__(self):
+        self.rec = self.blk = self.own = self.wf = self.drop_cfg = None
+        self.lean = self.needs_x = False
+        self.n_lab = self.B = 0
+        self.top = None   # (nh, d_skip, d_up3_head) once BackbonePairTopFn.backward has run
+
+
+class BackbonePairLowFn(torch.autograd.Function):
+    """BackbonePairFn cut in two autograd nodes, lower part: (x, n_lab, drop_cfg, state, top conv weights' shapes, *28 params of
+    conv1..conv4, center, up_concat4, up_concat3) -> (center_lab, center_unlab, up4_lab, up4_unlab, up3_lab, up3_unlab, link).
+
+    Why two nodes: the ICL heads read center / up4 / up3 only.  With the upper decoder levels (up_concat2, up_concat1, final: the
+    48^3 and 96^3 layers, about half of the backbone's time) in a node of their own, the heads' ~650 small kernels run on side streams
+    next to them in the forward pass, and the heads' backward runs next to the upper levels' backward (icl_b200/lanes.py).  Same
+    kernels on the same inputs as the single node.  `link` is a one-element tensor whose only purpose is the autograd edge that makes
+    the top node's backward run before this node's; the gradients the top section produces for this section travel on the state."""
+
+    @staticmethod
+    def forward(ctx, x, n_lab, drop_cfg, st, top_weights, *params_low):
+        ctx.set_materialize_grads(False)
+        center, up4, up3 = _forward_low(st, x, drop_cfg, params_low, top_weights)
+        st.n_lab, st.B = int(n_lab), center.shape[0]
+        ctx.st = st
+        v = ops.to_ncdhw_view
+        n = st.n_lab
+        link = torch.empty((1,), dtype=torch.float32, device=center.device)
+        return (v(center[:n]), v(center[n:]), v(up4[:n]), v(up4[n:]), v(up3[:n]), v(up3[n:]), link)
+
+    @staticmethod
+    def backward(ctx, gcl, gcu, g4l, g4u, g3l, g3u, glink):
+        st = ctx.st
+        nh, d_skip, d_up3_head = st.top if st.top is not None else (0, {"conv1": None, "conv2": None}, None)
+        gl, dx_in = _pair_bwd_low(st, st.n_lab, st.B, nh, d_skip, d_up3_head, gcl, gcu, g4l, g4u, g3l, g3u)
+        st.rec = st.top = None
+        return (dx_in, None, None, None, None) + tuple(_flat(gl, LOW_BLOCKS))
+
+
+class BackbonePairTopFn(torch.autograd.Function):
+    """Upper part: (link, state, *10 params of up_concat2, up_concat1, final) -> (final_lab, final_unlab)."""
+
+    @staticmethod
+    def forward(ctx, link, st, *params_top):
+        ctx.set_materialize_grads(False)
+        final = _forward_top(st, params_top)
+        ctx.st = st
+        v = ops.to_ncdhw_view
+        n = st.n_lab
+        return v(final[:n]), v(final[n:])
+
+    @staticmethod
+    def backward(ctx, gfl, gfu):
+        st = ctx.st
+        gt, nh, d_skip, d_up3_head = _pair_bwd_top(st, st.n_lab, st.B, gfl, gfu)
+        st.top = (nh, d_skip, d_up3_head)
+        return (None, None) + tuple(_flat(gt, TOP_BLOCKS, with_final=True))

@@ -2,7 +2,7 @@
 import torch
 import torch.nn as nn
 
-from .backbone3d import Backbone3DFn, BackbonePairFn
+from .backbone3d import N_LOW, Backbone3DFn, BackbonePairFn, BackbonePairLowFn, BackbonePairTopFn, _PairState
 from .utils import UnetConv3, UnetUp3_CT, _kaiming
 
 
@@ -59,9 +59,7 @@ class _Backbone3DModule(nn.Module):
             raise RuntimeError("icl_b200 networks run on CUDA tensors only (no CPU fallback)")
         return Backbone3DFn.apply(x, self._drop_cfg(), *self._backbone_params())
 
-    def _run_pair(self, x_lab, x_unlab):
-        """Labeled and unlabeled pass as one batched pass (backbone3d.BackbonePairFn).  Returns
-        ((final, center, up4, up3) of the labeled samples, the same for the unlabeled samples)."""
+    def _pair_cfg(self, x_lab, x_unlab):
         if not (x_lab.is_cuda and x_unlab.is_cuda):
             raise RuntimeError("icl_b200 networks run on CUDA tensors only (no CPU fallback)")
         cfg_l = self._drop_cfg()
@@ -70,8 +68,30 @@ class _Backbone3DModule(nn.Module):
             # explicit keep-masks (test hook): two per pass in the reference's order (labeled pass first), joined along the batch
             cfg_u = self._drop_cfg()
             cfg = (cfg_l[0], torch.cat([cfg_l[1], cfg_u[1]]), torch.cat([cfg_l[2], cfg_u[2]]), 0, 0)
+        return cfg
+
+    def _run_pair(self, x_lab, x_unlab):
+        """Labeled and unlabeled pass as one batched pass (backbone3d.BackbonePairFn).  Returns
+        ((final, center, up4, up3) of the labeled samples, the same for the unlabeled samples)."""
+        cfg = self._pair_cfg(x_lab, x_unlab)
         o = BackbonePairFn.apply(torch.cat([x_lab, x_unlab]), x_lab.shape[0], cfg, *self._backbone_params())
         return (o[0], o[2], o[4], o[6]), (o[1], o[3], o[5], o[7])
+
+    def _run_pair_low(self, x_lab, x_unlab):
+        """The batched pass up to up3 as an autograd node of its own (backbone3d.BackbonePairLowFn).  Returns
+        ((center, up4, up3) of the labeled samples, the same for the unlabeled samples, handle for _run_pair_top)."""
+        cfg = self._pair_cfg(x_lab, x_unlab)
+        ps = self._backbone_params()
+        st = _PairState()
+        o = BackbonePairLowFn.apply(torch.cat([x_lab, x_unlab]), x_lab.shape[0], cfg, st, [w.detach() for w in ps[N_LOW:N_LOW + 8:2]],
+                                    *ps[:N_LOW])
+        return (o[0], o[2], o[4]), (o[1], o[3], o[5]), (o[6], st, ps[N_LOW:])
+
+    @staticmethod
+    def _run_pair_top(handle):
+        """up_concat2, up_concat1, final on top of _run_pair_low: (final_lab, final_unlab)."""
+        link, st, ps = handle
+        return BackbonePairTopFn.apply(link, st, *ps)
 
 
 class unet_3D(_Backbone3DModule):

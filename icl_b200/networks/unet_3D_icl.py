@@ -9,6 +9,7 @@ import torch
 import torch.nn as nn
 
 from .. import functional as Fn
+from .. import lanes as Ln
 from .unet_3D import _Backbone3DModule
 
 
@@ -108,18 +109,33 @@ class Class_Decoder(nn.Module):
     def _r(self, B, device):
         return self.drop_path.sample(B, device) if isinstance(self.drop_path, DropPath) else None
 
+    def draws(self, B, device):
+        """The four DropPath scales of one call, drawn in the reference's order: q+dp(q), q+dp(mlp), a+dp(a), a+dp(mlp2)  (:264-267)."""
+        return [self._r(B, device) for _ in range(4)]
+
+    # The forward pass in independent pieces, so that InherentConsistent can put them on different lanes (icl_b200/lanes.py):
+    # kv() and ql() feed the attention, q_branch() and attn_branch() consume its two outputs and do not see each other.
+    def kv(self, feat):
+        return Fn.linear(Fn.layer_norm(feat, self.norm1.weight, self.norm1.bias, self.norm1.eps), self.attn.fc_kv.weight, self.attn.fc_kv.bias)
+
+    def ql(self, query):
+        n = self.norm1_query
+        return Fn.linear(Fn.layer_norm(query, n.weight, n.bias, n.eps), self.attn.fc_q.weight, self.attn.fc_q.bias)
+
+    def q_branch(self, xv, rs):
+        q = Fn.linear(xv, self.attn.proj.weight, self.attn.proj.bias)
+        q = Fn.add_scaled(q, q, rs[0])
+        return Fn.add_scaled(q, self.mlp(Fn.layer_norm(q, self.norm2.weight, self.norm2.bias, self.norm2.eps)), rs[1])
+
+    def attn_branch(self, attn, rs):
+        attn = Fn.add_scaled(attn, attn, rs[2])
+        return Fn.add_scaled(attn, self.mlp2(Fn.layer_norm(attn, self.norm3.weight, self.norm3.bias, self.norm3.eps)), rs[3])
+
     def forward(self, query, feat, need_query=True):
-        B, dev = feat.shape[0], feat.device
-        ln = lambda t, m: Fn.layer_norm(t, m.weight, m.bias, m.eps)
-        q, attn = self.attn(ln(query, self.norm1_query), ln(feat, self.norm1), need_query)
-        # the reference draws DropPath in this order: q+dp(q), q+dp(mlp), a+dp(a), a+dp(mlp2)  (:264-267)
-        r1, r2 = self._r(B, dev), self._r(B, dev)
-        if need_query:
-            q = Fn.add_scaled(q, q, r1)
-            q = Fn.add_scaled(q, self.mlp(ln(q, self.norm2)), r2)
-        attn = Fn.add_scaled(attn, attn, self._r(B, dev))
-        attn = Fn.add_scaled(attn, self.mlp2(ln(attn, self.norm3)), self._r(B, dev))
-        return q, attn
+        rs = self.draws(feat.shape[0], feat.device)
+        xv, attn = Fn.proxy_attention(self.ql(query), self.kv(feat), self.attn.num_heads, want_xv=need_query)
+        q = self.q_branch(xv, rs) if need_query else None
+        return q, self.attn_branch(attn, rs)
 
 
 class SeparableConv3d(nn.Module):
@@ -176,10 +192,14 @@ class InherentConsistent(nn.Module):
             self.query_convs.append(nn.Conv1d(in_chans[i], in_chans[i] // 2, kernel_size=1, stride=1, padding=0))
         self.guided_Q = nn.Parameter(torch.zeros(1, num_classes, in_chans[0]))
 
-    def forward(self, feats, guided_Q=None, modal="labeled", need_queries=True):
+    def forward(self, feats, guided_Q=None, modal="labeled", need_queries=True, lanes=None):
         """`need_queries=False` (our extension, default keeps reference behaviour) skips the softmax.V / proj /
         mlp / query_convs branch when the caller discards updated_Qs in 'unlabeled' mode — that branch is
-        dead in the reference's graph (unet_3D_icl.py:147) and its parameters keep grad None."""
+        dead in the reference's graph (unet_3D_icl.py:147) and its parameters keep grad None.
+
+        `lanes` (our extension): {"main", "q", "s": [one stream per scale]} from icl_b200.lanes — the token / attention-map work of
+        scale i is enqueued on lanes["s"][i], the query chain on lanes["q"]; the returned tensors are then NOT yet ordered with
+        respect to the caller's stream: the caller joins the lanes (unet_3D_icl.forward does).  None: everything on the current stream."""
         feat_maps, updated_Qs = [], []
         BS = feats[0].shape[0]
         if modal not in ("labeled", "unlabeled"):
@@ -187,27 +207,43 @@ class InherentConsistent(nn.Module):
         Fn.defer_batch_counters()
         labeled = modal == "labeled"
         need_q = need_queries or labeled
+        main = lanes["main"] if lanes else None
+        lq = lanes["q"] if lanes else None
+        # every DropPath scale of this pass first, in the reference's order (scale by scale), on the caller's stream
+        draws = [self.class_decoders[i].draws(BS, feats[i].device) for i in range(len(self.depth))]
         next_Q = self.guided_Q.expand(BS, -1, -1) if labeled else None
+        Ln.handoff(lq, main, *[r for rs in draws for r in rs[:2]])
         for i in range(len(self.depth)):
             f = feats[i]
             B, C, d, h, w = f.shape
-            pl = self.proj_layers[i]
-            # 1x1x1 conv on channels-last rows == Linear; flatten(2).transpose(1,2) is free in NDHWC
-            tok = Fn.linear(f.permute(0, 2, 3, 4, 1).reshape(B, d * h * w, C), pl.weight.reshape(C, C), pl.bias)
-            nl = self.norm_layers[i]
-            tok = Fn.layer_norm(tok, nl.weight, nl.bias, nl.eps)
-            q_in = next_Q if labeled else guided_Q[i].expand(BS, -1, -1)
-            q, attn = self.class_decoders[i](q_in, tok, need_q)
-            bs, K, H, N = attn.shape
-            a = attn.reshape(bs * K, H, d, h, w)
-            a = self.attn_convs0[i](a)
-            c1 = self.attn_convs1[i]
-            fm = Fn.planar_pointwise(a, c1.weight, c1.bias).reshape(bs, K, d, h, w)
-            feat_maps.append(fm)
+            ls = lanes["s"][i] if lanes else None
+            dec, rs = self.class_decoders[i], draws[i]
+            Ln.handoff(ls, main, f, *rs[2:])
+            with Ln.on(ls):
+                pl = self.proj_layers[i]
+                # 1x1x1 conv on channels-last rows == Linear; flatten(2).transpose(1,2) is free in NDHWC
+                tok = Fn.linear(f.permute(0, 2, 3, 4, 1).reshape(B, d * h * w, C), pl.weight.reshape(C, C), pl.bias)
+                nl = self.norm_layers[i]
+                kv = dec.kv(Fn.layer_norm(tok, nl.weight, nl.bias, nl.eps))
+            with Ln.on(lq):
+                ql = dec.ql(next_Q if labeled else guided_Q[i].expand(BS, -1, -1))
+            Ln.handoff(ls, lq, ql)
+            with Ln.on(ls):
+                xv, attn = Fn.proxy_attention(ql, kv, dec.attn.num_heads, want_xv=need_q)
             if need_q:
-                qc = self.query_convs[i]
-                next_Q = Fn.linear(q, qc.weight[:, :, 0], qc.bias)
-                updated_Qs.append(Fn.batch_mean(q))
+                Ln.handoff(lq, ls, xv)
+                with Ln.on(lq):
+                    q = dec.q_branch(xv, rs)
+                    qc = self.query_convs[i]
+                    next_Q = Fn.linear(q, qc.weight[:, :, 0], qc.bias)
+                    updated_Qs.append(Fn.batch_mean(q))
+            with Ln.on(ls):
+                attn = dec.attn_branch(attn, rs)
+                bs, K, H, N = attn.shape
+                a = attn.reshape(bs * K, H, d, h, w)
+                a = self.attn_convs0[i](a)
+                c1 = self.attn_convs1[i]
+                feat_maps.append(Fn.planar_pointwise(a, c1.weight, c1.bias).reshape(bs, K, d, h, w))
         Fn.flush_batch_counters()   # num_batches_tracked of the BatchNorms above: one multi-tensor add
         return feat_maps, updated_Qs
 
@@ -226,17 +262,41 @@ class unet_3D_icl(_Backbone3DModule):
     def forward(self, x_lab, x_unlab=None, inference=None):
         if inference:
             return self._run(x_lab)[0]
-        if os.environ.get("ICL_DISABLE_PAIR") == "1" or x_lab.shape[1:] != x_unlab.shape[1:]:
-            final_lab, center_lab, up4_lab, up3_lab = self._run(x_lab)
-            final_unlab, center_unlab, up4_unlab, up3_unlab = self._run(x_unlab)
-        else:
-            # both passes share every weight and InstanceNorm is per sample: one batched pass, same values
-            (final_lab, center_lab, up4_lab, up3_lab), (final_unlab, center_unlab, up4_unlab, up3_unlab) = self._run_pair(x_lab, x_unlab)
-        feats_lab = [center_lab, up4_lab, up3_lab]
-        feats_unlab = [center_unlab, up4_unlab, up3_unlab]
-        feat_Maps_lab, updated_Qs_lab = self.sspa(feats_lab, "labeled")
-        feat_Maps_consis, _ = self.sspa(feats_unlab, "labeled")
-        feat_Maps_unlab, _ = self.uscl(feats_unlab, updated_Qs_lab, "unlabeled", need_queries=False)
+        dev = x_lab.device
+        pair = os.environ.get("ICL_DISABLE_PAIR") != "1" and x_lab.shape[1:] == x_unlab.shape[1:]
+        if not (pair and Ln.enabled(dev)):
+            if pair:
+                # both passes share every weight and InstanceNorm is per sample: one batched pass, same values
+                (final_lab, center_lab, up4_lab, up3_lab), (final_unlab, center_unlab, up4_unlab, up3_unlab) = self._run_pair(x_lab, x_unlab)
+            else:
+                final_lab, center_lab, up4_lab, up3_lab = self._run(x_lab)
+                final_unlab, center_unlab, up4_unlab, up3_unlab = self._run(x_unlab)
+            feats_lab = [center_lab, up4_lab, up3_lab]
+            feats_unlab = [center_unlab, up4_unlab, up3_unlab]
+            feat_Maps_lab, updated_Qs_lab = self.sspa(feats_lab, "labeled")
+            feat_Maps_consis, _ = self.sspa(feats_unlab, "labeled")
+            feat_Maps_unlab, _ = self.uscl(feats_unlab, updated_Qs_lab, "unlabeled", need_queries=False)
+            return final_lab, final_unlab, feat_Maps_lab, feat_Maps_unlab, feat_Maps_consis
+        # Lanes (icl_b200/lanes.py).  The batched backbone pass is two autograd nodes: the heads only read center / up4 / up3, so they
+        # are enqueued on side streams right after the lower node and run next to up_concat2 / up_concat1 / final (forward) and next
+        # to those layers' backward.  Per-scale lanes s0..s2 are shared by the two sspa passes (same BatchNorm modules: same lane, so
+        # their running statistics are updated in the reference's order), the query chain has a lane, and the uscl pass, which only
+        # waits for the labeled pass's updated proxies, has lanes of its own.
+        feats_lab, feats_unlab, top = self._run_pair_low(x_lab, x_unlab)
+        L = Ln.get(dev, ["q", "s0", "s1", "s2", "uq", "u0", "u1", "u2"])
+        main = L["main"]
+        la = {"main": main, "q": L["q"], "s": [L["s0"], L["s1"], L["s2"]]}
+        lu = {"main": main, "q": L["uq"], "s": [L["u0"], L["u1"], L["u2"]]}
+        feat_Maps_lab, updated_Qs_lab = self.sspa(list(feats_lab), "labeled", lanes=la)
+        Ln.handoff(L["uq"], L["q"], *updated_Qs_lab)
+        feat_Maps_consis, _ = self.sspa(list(feats_unlab), "labeled", lanes=la)
+        feat_Maps_unlab, _ = self.uscl(list(feats_unlab), updated_Qs_lab, "unlabeled", need_queries=False, lanes=lu)
+        final_lab, final_unlab = self._run_pair_top(top)
+        for k, s in L.items():
+            if k != "main":
+                Ln.handoff(main, s)
+        for t in feat_Maps_lab + feat_Maps_unlab + feat_Maps_consis:
+            t.record_stream(main)
         return final_lab, final_unlab, feat_Maps_lab, feat_Maps_unlab, feat_Maps_consis
 
     @staticmethod

@@ -8,7 +8,7 @@ entirely (no weight decay, no momentum) exactly like torch.  One kernel launch p
 import numpy as np
 import torch
 
-from . import _lib, ops
+from . import _lib, lanes, ops
 from .ops import P, c_f, c_int, call
 
 
@@ -130,6 +130,7 @@ class SGD(torch.optim.Optimizer):
         if closure is not None:
             with torch.enable_grad():
                 loss = closure()
+        lanes.join_all()   # gradients / factor lists produced on the ICL-head lanes (no-op when no lane exists)
         for gi, group in enumerate(self.param_groups):
             rows, keep = [], []
             for p in group["params"]:

@@ -21,6 +21,8 @@ GradAverager.average() joins the side stream and copies the averaged buckets bac
 import torch
 import torch.distributed as dist
 
+from . import lanes
+
 FACTOR_MIN_NUMEL = 1 << 24  # weights at least this large are exchanged as factors
 
 _CTX = {"world": 1, "group": None, "factored_ids": set(), "comm": None, "overlap": False}
@@ -151,6 +153,7 @@ class GradAverager:
         if not todo:
             b.inflight = (None, [])
             return
+        lanes.join_all()   # a bucket's gradients may have been accumulated on different ICL-head lanes
         flat = torch.cat([p.grad.reshape(-1) for p in todo])
         comm = _comm_stream()
         if comm is not None:
