@@ -451,6 +451,8 @@ def measure_train(a, wl, rank, world, dev, local, full=True):
         "vs_baseline": None, "dtype": "bf16x3+fp32" if a.precision == "parity" else "bf16+fp32", "data": "synthetic",
         "config": {"workload": tb.cfg["desc"], "global_batch": BATCH * world, "parallelism": "dp%d" % world, "precision_mode": a.precision,
                    "launch": "cuda-graph replay of the whole step" if use_graph else "eager",
+                   "streams": "ICL heads on 8 side streams next to the upper decoder levels (same kernels, same values)"
+                              if os.environ.get("ICL_HEAD_LANES", "1") != "0" else "one stream",
                    "exchange": None if world == 1 else ("bucketed all-reduce + mlp2 factor all-gathers on a side stream, overlapped with backward"
                                                         if not a.no_overlap else "after backward"),
                    "l2": "no flush needed: per-step working set (785M params + activations, >15 GB) >> 126 MB L2"},
@@ -497,12 +499,28 @@ def measure_train(a, wl, rank, world, dev, local, full=True):
     # ---- where the REPLAYED step spends its time: CUPTI kernel records of `steps` more replays (outside the timed region).  The eager
     # event pass below times every launch with the host in the loop, which inflates kernels of a few microseconds; the kernel that
     # dominates the step is therefore chosen from these records, its roofline from the CUDA-event duration of the same kernel.
+    # The timed step runs the ICL heads on side streams next to the backbone (icl_b200/lanes.py); kernels that share the GPU stretch
+    # each other, so their durations inside that step say nothing about the kernels themselves.  Every per-kernel number below is
+    # therefore taken from the SAME step issued on ONE stream (ICL_HEAD_LANES=0: same kernels, same inputs, serial order), which
+    # is also timed (`single_stream`).
     graph_kernels = None
-    if rank == 0 and not a.no_profile:
-        graph_kernels = cupti_kernel_times(lambda: tb.step(tb.x_dev, tb.y_dev), min(a.steps, 5))
-    elif not a.no_profile:
-        for _ in range(min(a.steps, 5)):   # the other ranks step along (collectives)
-            tb.step(tb.x_dev, tb.y_dev)
+    lanes_prev = os.environ.get("ICL_HEAD_LANES")
+    if not a.no_profile:
+        os.environ["ICL_HEAD_LANES"] = "0"
+        if use_graph:
+            tb.graphed.release()
+            tb.graphed = None
+            tb.capture()
+            for _ in range(3):
+                tb.step(tb.x_dev, tb.y_dev)
+            line["single_stream"] = {"ms_per_step": timer(lambda: tb.step(tb.x_dev, tb.y_dev), a.steps),
+                                     "note": "the same step with the ICL-head lanes off (every kernel on one stream); the per-kernel "
+                                             "breakdowns (kernels, graph_kernels, conv_tensor_util, hbm_kernels, roofline) are measured on it"}
+        if rank == 0:
+            graph_kernels = cupti_kernel_times(lambda: tb.step(tb.x_dev, tb.y_dev), min(a.steps, 5))
+        else:
+            for _ in range(min(a.steps, 5)):   # the other ranks step along (collectives)
+                tb.step(tb.x_dev, tb.y_dev)
 
     # ---- per-kernel breakdown (CUDA events around every launch of our kernels), separate eager pass in this same run
     prof = None
@@ -515,6 +533,10 @@ def measure_train(a, wl, rank, world, dev, local, full=True):
         torch.cuda.synchronize()
         if rank == 0:
             prof = ops.profile_stop(nprof)
+    if lanes_prev is None:
+        os.environ.pop("ICL_HEAD_LANES", None)
+    else:
+        os.environ["ICL_HEAD_LANES"] = lanes_prev
     if rank == 0 and prof is not None and a.detail:
         os.makedirs(os.path.dirname(os.path.abspath(a.detail)), exist_ok=True)
         json.dump(prof["detail"], open(a.detail, "w"), indent=1)

@@ -286,6 +286,8 @@ def test_maxpool_ties_first_max():
     out_ref.backward(dout)
     out, idx, pk = ops.maxpool_fwd(cl(x), True)
     assert torch.equal(uncl(out), out_ref.detach())
+    rec = (pk[0].float() + pk[1].float()).permute(0, 1, 5, 2, 3, 4).reshape(B, C, D // 2, H // 2, W // 2).cpu()
+    assert torch.equal(rec, out_ref.detach()), "maxpool PK hi+lo"
     dx = torch.empty(B, D, H, W, C, device="cuda")
     ops.maxpool_bwd(cl(dout), idx, dx, False)
     assert torch.equal(uncl(dx), xr.grad)
