@@ -49,7 +49,13 @@ class LinearFn(torch.autograd.Function):
                     gd, xd, ev, keep = parallel.gather_factors_async(g, x2, dp["group"])
                     sink.append((gd, xd, 1.0 / dp["world"], ev, keep))
                 else:
-                    sink.append((g, x2, 1.0, None, None))
+                    # the event lets the optimizer start this weight's update as soon as its last factor pair exists (optim.SGD
+                    # may run the update on a lane of its own, next to the rest of backward)
+                    ev = None
+                    if g.is_cuda:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                    sink.append((g, x2, 1.0, ev, None))
                 if ctx.has_bias:
                     db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
                     call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))

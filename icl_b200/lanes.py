@@ -23,14 +23,15 @@ def enabled(device):
     return device.type == "cuda" and os.environ.get("ICL_HEAD_LANES", "1") != "0"
 
 
-def get(device, names):
-    """{name: stream} of cached high-priority side streams on `device` (+ "main": the current stream)."""
+def get(device, names, priority=-1):
+    """{name: stream} of cached side streams on `device` (+ "main": the current stream).  priority -1: scheduled ahead of the caller's
+    stream (the heads' small kernels slip in between the backbone's large ones); 0: same as the caller's."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     out = {"main": torch.cuda.current_stream(device)}
     for n in names:
         s = _STREAMS.get((idx, n))
         if s is None:
-            s = _STREAMS[(idx, n)] = torch.cuda.Stream(device=device, priority=-1)
+            s = _STREAMS[(idx, n)] = torch.cuda.Stream(device=device, priority=priority)
         out[n] = s
     return out
 

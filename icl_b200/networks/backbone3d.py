@@ -11,8 +11,11 @@ reproduces the reference's autograd pruning exactly — a branch whose `final` l
 (the unlabeled pass) skips the up_concat2/up_concat1/final backward and returns None for
 their parameters, so `.grad is None`-ness (and therefore SGD weight-decay behaviour) matches.
 """
+import os
+
 import torch
 
+from .. import lanes as Ln
 from .. import ops
 
 PARAM_BLOCKS = ["conv1", "conv2", "conv3", "conv4", "center", "up_concat4.conv", "up_concat3.conv", "up_concat2.conv",
@@ -78,6 +81,18 @@ def _half_prefix(h, n):
     return q
 
 
+def _wgrad_lane(device):
+    if os.environ.get("ICL_WGRAD_LANE", "1") == "0" or not Ln.enabled(device):
+        return None, None
+    L = Ln.get(device, ["w"], priority=0)
+    return L["w"], L["main"]
+
+
+def _wgrad_join(device):
+    wl, main = _wgrad_lane(device)
+    Ln.handoff(main, wl)
+
+
 def _half_bwd(h, dA, need_dx, dx_out0=None):
     """Returns (dw, db, [dx per source] or None).  dx_out0: optional preallocated tensor for the gradient of the FIRST source."""
     cins = [s.C for s in h.srcs]
@@ -88,7 +103,14 @@ def _half_bwd(h, dA, need_dx, dx_out0=None):
     if wgrad_umma:
         # fp32 dY is only read by the CUDA-core data-gradient fallback
         dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, True, want_dbias=True, want_f32=need_dx and not dgrad_umma)
-        dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W, bx=h.pk_bs)
+        # the weight gradient is a leaf of the backward chain: it runs on a lane of its own next to the data gradient that continues
+        # the chain (at the deep levels neither fills the GPU alone); the caller joins the lane before backward returns (_wgrad_join)
+        wl, main = _wgrad_lane(dY_pk.device)
+        Ln.handoff(wl, main, dY_pk)
+        with Ln.on(wl):
+            dw = ops.conv3d_wgrad_umma([s.pk for s in h.srcs], cins, dY_pk, cout, B, D, H, W, bx=h.pk_bs)
+        if wl is not None:
+            dw.record_stream(main)
     elif ops.stem_ok(cins, cout):
         dY, dY_pk, db = ops.instnorm_relu_bwd(dA, h.y, h.mr, dgrad_umma, want_dbias=True)
         dw = ops.conv3d_stem_wgrad(h.srcs[0].f32, dY, B, D, H, W)
@@ -319,6 +341,7 @@ class Backbone3DFn(torch.autograd.Function):
             out += grads.get(name, [None, None, None, None])
         out += grads.get("final", [None, None])
         ctx.rec = None
+        _wgrad_join(wf2.device)
         return (dx_in, None) + tuple(out)
 
 
@@ -492,6 +515,7 @@ class BackbonePairFn(torch.autograd.Function):
         gl, dx_in = _pair_bwd_low(ctx, nl, B, nh, d_skip, d_up3_head, gcl, gcu, g4l, g4u, g3l, g3u)
         gl.update(gt)
         ctx.rec = None
+        _wgrad_join(ctx.wf.device)
         return (dx_in, None, None) + tuple(_flat(gl, PARAM_BLOCKS, with_final=True))
 
 
@@ -533,6 +557,7 @@ class BackbonePairLowFn(torch.autograd.Function):
         nh, d_skip, d_up3_head = st.top if st.top is not None else (0, {"conv1": None, "conv2": None}, None)
         gl, dx_in = _pair_bwd_low(st, st.n_lab, st.B, nh, d_skip, d_up3_head, gcl, gcu, g4l, g4u, g3l, g3u)
         st.rec = st.top = None
+        _wgrad_join(st.wf.device)
         return (dx_in, None, None, None, None) + tuple(_flat(gl, LOW_BLOCKS))
 
 
@@ -553,4 +578,5 @@ class BackbonePairTopFn(torch.autograd.Function):
         st = ctx.st
         gt, nh, d_skip, d_up3_head = _pair_bwd_top(st, st.n_lab, st.B, gfl, gfu)
         st.top = (nh, d_skip, d_up3_head)
+        _wgrad_join(st.wf.device)
         return (None, None) + tuple(_flat(gt, TOP_BLOCKS, with_final=True))

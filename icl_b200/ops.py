@@ -461,7 +461,7 @@ def row_combine(a, sa, b, sb, rows):
     return out
 
 
-def sgd_factored(p, m, factors, lr, mu, wd):
+def sgd_factored(p, m, factors, lr, mu, wd, max_ctas=0):
     """Momentum-SGD update of a huge 2-D weight from its rank-R gradient factors [(dy [r,N], x [r,K], scale), ...]:
     g = sum dy^T x (+ wd p), m = mu m + g, p -= lr m.  tcgen05 path when the shape allows, CUDA-core kernel otherwise."""
     N, K = p.shape
@@ -472,7 +472,7 @@ def sgd_factored(p, m, factors, lr, mu, wd):
         for dy, x, scale in factors:
             call("icl_sgd_factored_pack", P(dy), P(x), c_int(dy.shape[0]), c_int(r0), c_int(R), c_int(N), c_int(K), c_f(scale), P(ws))
             r0 += dy.shape[0]
-        call("icl_sgd_factored_apply", c_int(R), c_int(N), c_int(K), P(ws), P(p), P(m), P(lr), c_f(mu), c_f(wd), c_int(_MAX_CTAS),
+        call("icl_sgd_factored_apply", c_int(R), c_int(N), c_int(K), P(ws), P(p), P(m), P(lr), c_f(mu), c_f(wd), c_int(max_ctas or _MAX_CTAS),
              mbytes=16e-6 * p.numel(), gflop=2e-9 * R * N * K, tag="R%d %dx%d" % (R, N, K))
     else:
         dy = torch.cat([f[0] * f[2] if f[2] != 1.0 else f[0] for f in factors], 0).contiguous()

@@ -36,7 +36,9 @@ def _worker(rank, world, port, q):
         d = dy_.t() @ x_
         return d if acc is None else acc + d
     dW = parallel.averaged_factored_wgrad(dy, x, wgrad)
-    q.put((rank, grads, dy, x, dW))
+    # numpy payloads travel by value: a tensor would be shared through a file descriptor served by this process, which may have
+    # exited before the parent receives it
+    q.put((rank, {k: (None if v is None else v.numpy()) for k, v in grads.items()}, dy.numpy(), x.numpy(), dW.numpy()))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -50,6 +52,8 @@ def test_grad_averager_and_factor_exchange_gloo():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
+    tt = lambda a: None if a is None else torch.from_numpy(a)
+    res = [(r[0], {k: tt(v) for k, v in r[1].items()}, tt(r[2]), tt(r[3]), tt(r[4])) for r in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
