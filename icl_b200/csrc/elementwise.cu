@@ -789,6 +789,34 @@ __global__ void __launch_bounds__(256) upsample2x_fwd_cl_k(const float* __restri
     if (hi) st_pk8(hi + (size_t)s * 8, write_lo ? hi + plane + (size_t)s * 8 : nullptr, r);
   }
 }
+// Thread -> (coarse voxel, channel quad) with a COMPACT 3-D tile of coarse voxels per 256-thread block (up to 4 x 4 x 2: x, y, z), the
+// quad fastest: the neighbourhoods of a block's voxels overlap, so most of their loads hit L1 (a linear sweep along x re-reads every
+// y / z neighbour from L2: 4x the compulsory traffic, which made the adjoint kernel L2-bound).  C/4 must be a power of two <= 256.
+struct Up2Tile { int b, z, y, x, q; bool valid; };
+__device__ __forceinline__ Up2Tile up2_tile(int C4, int d, int h, int w) {
+  const int vpb = 256 / C4;
+  const int tx = min(4, vpb), ty = min(4, vpb / tx), tz = vpb / (tx * ty);
+  const int ntx = cdiv(w, tx), nty = cdiv(h, ty), ntz = cdiv(d, tz);
+  int t = blockIdx.x;
+  const int bx = t % ntx; t /= ntx;
+  const int by = t % nty; t /= nty;
+  const int bz = t % ntz;
+  Up2Tile o;
+  o.b = t / ntz;
+  o.q = threadIdx.x % C4;
+  const int lv = threadIdx.x / C4;
+  o.x = bx * tx + lv % tx;
+  o.y = by * ty + (lv / tx) % ty;
+  o.z = bz * tz + lv / (tx * ty);
+  o.valid = o.x < w && o.y < h && o.z < d;
+  return o;
+}
+static inline long long up2_tile_blocks(int B, int C4, int d, int h, int w) {
+  const int vpb = 256 / C4;
+  const int tx = vpb < 4 ? vpb : 4, ty = (vpb / tx) < 4 ? (vpb / tx) : 4, tz = vpb / (tx * ty);
+  return (long long)B * cdiv(d, tz) * cdiv(h, ty) * cdiv(w, tx);
+}
+static inline bool up2_tile_ok(int C) { const int c4 = C / 4; return C % 8 == 0 && c4 <= 256 && (c4 & (c4 - 1)) == 0; }
 // Thread = one COARSE voxel x 4 channels (channel quad fastest across lanes): the 27 coarse neighbours are loaded once (float4 each,
 // fully coalesced: a warp reads whole 128-byte lines) and all 8 fine voxels of the cell are formed from them, 3.4 loads per fine voxel
 // instead of 8 (the per-fine-voxel kernels above are bound by L1 load wavefronts).  Arithmetic per output is ATen's, in ATen's order:
@@ -800,12 +828,15 @@ __device__ __forceinline__ float4 lerp4(float l, const float4& a, const float4& 
 }
 __device__ __forceinline__ float4 sel4(bool c, const float4& a, const float4& b) { return c ? a : b; }
 __global__ void __launch_bounds__(256, 2) upsample2x_fwd_c27_k(const float* __restrict__ x, float* __restrict__ out, __nv_bfloat16* __restrict__ pk,
-                                                            int write_lo, int B, int C, int d, int h, int w) {
+                                                               int write_lo, int B, int C, int d, int h, int w) {
   const int D = 2 * d, H = 2 * h, W = 2 * w, C4 = C >> 2, C8 = C >> 3;
   const size_t S = (size_t)D * H * W;
   const size_t plane = (size_t)B * C8 * S * 8;
   const unsigned total = (unsigned)B * d * h * w * C4;            // host guarantees < 2^31, C4 even: lane pairs never straddle the end
   const unsigned nthreads = gridDim.x * blockDim.x;
+  const float4* __restrict__ x4 = reinterpret_cast<const float4*>(x);
+  // (a linear sweep, x fastest: the compact tiles of the adjoint kernel below made THIS kernel slower — it is bound by instruction
+  // issue, not by L2, and one short-lived block per tile costs more than the grid-stride loop)
   for (unsigned i0 = blockIdx.x * blockDim.x + threadIdx.x; i0 - (threadIdx.x & 31) < total; i0 += nthreads) {
     const bool valid = i0 < total;
     const unsigned i = valid ? i0 : total - 1;
@@ -815,34 +846,40 @@ __global__ void __launch_bounds__(256, 2) upsample2x_fwd_c27_k(const float* __re
     const int cy = (int)(v % (unsigned)h); v /= (unsigned)h;
     const int cz = (int)(v % (unsigned)d);
     const int b = (int)(v / (unsigned)d);
-    const int xs[3] = {max(cx - 1, 0), cx, min(cx + 1, w - 1)};
-    const int ys[3] = {max(cy - 1, 0), cy, min(cy + 1, h - 1)};
-    const int zs[3] = {max(cz - 1, 0), cz, min(cz + 1, d - 1)};
-    // fine index 2c: neighbours (c-1, c) with weight .75 on c — at c = 0 up2_src clamps to (0, 1) with weight 0;
-    // fine index 2c+1: (c, c+1) with weight .25 (c+1 clamped at the end)
-    const bool ix = cx > 0, iy = cy > 0, iz = cz > 0;
-    const float lx0 = ix ? 0.75f : 0.f, ly0 = iy ? 0.75f : 0.f, lz0 = iz ? 0.75f : 0.f;
-    const float* xb = x + (size_t)b * d * h * w * C + q * 4;
+    // Neighbours clamped to the volume.  Fine index 2c blends (c-1, c) with weight .75 on c; at c = 0 up2_src clamps to (0, 1) with
+    // weight 0, i.e. the value of voxel 0 itself: with the clamped neighbour (voxel 0 again) and weight 0 that is (1-0)*v0 + 0*v0,
+    // the same number.  Fine index 2c+1 blends (c, c+1) with weight .25, c+1 clamped at the end (up2_src does the same).
+    const float lx0 = cx > 0 ? 0.75f : 0.f, ly0 = cy > 0 ? 0.75f : 0.f, lz0 = cz > 0 ? 0.75f : 0.f;
+    // offsets in float4 units (host guarantees the coarse tensor has < 2^31 floats)
+    const unsigned xo[3] = {(unsigned)max(cx - 1, 0) * C4, (unsigned)cx * C4, (unsigned)min(cx + 1, w - 1) * C4};
+    const unsigned yo[3] = {(unsigned)max(cy - 1, 0) * w * C4, (unsigned)cy * w * C4, (unsigned)min(cy + 1, h - 1) * w * C4};
+    const unsigned hw = (unsigned)h * w * C4;
+    const unsigned zo[3] = {(unsigned)max(cz - 1, 0) * hw, (unsigned)cz * hw, (unsigned)min(cz + 1, d - 1) * hw};
+    const float4* xb = x4 + (size_t)b * d * hw + q;
     float4 P[3][2][2];   // [coarse plane][fine dy][fine dx]: h-lerp of w-lerps
 #pragma unroll
     for (int kz = 0; kz < 3; ++kz) {
       float4 vx[3][2];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
-        const float* row = xb + ((size_t)zs[kz] * h + ys[ky]) * w * C;
-        const float4 n0 = *reinterpret_cast<const float4*>(row + (size_t)xs[0] * C);
-        const float4 n1 = *reinterpret_cast<const float4*>(row + (size_t)xs[1] * C);
-        const float4 n2 = *reinterpret_cast<const float4*>(row + (size_t)xs[2] * C);
-        vx[ky][0] = lerp4(lx0, sel4(ix, n0, n1), sel4(ix, n1, n2));
+        const float4* row = xb + (zo[kz] + yo[ky]);
+        const float4 n0 = row[xo[0]], n1 = row[xo[1]], n2 = row[xo[2]];
+        vx[ky][0] = lerp4(lx0, n0, n1);
         vx[ky][1] = lerp4(0.25f, n1, n2);
       }
 #pragma unroll
       for (int dx = 0; dx < 2; ++dx) {
-        P[kz][0][dx] = lerp4(ly0, sel4(iy, vx[0][dx], vx[1][dx]), sel4(iy, vx[1][dx], vx[2][dx]));
+        P[kz][0][dx] = lerp4(ly0, vx[0][dx], vx[1][dx]);
         P[kz][1][dx] = lerp4(0.25f, vx[1][dx], vx[2][dx]);
       }
     }
     const int odd = q & 1;
+    // 32-bit element offsets (host guarantees B*C*S < 2^31)
+    const unsigned S32 = (unsigned)D * H * W;
+    const unsigned s00 = ((unsigned)(2 * cz) * H + 2 * cy) * W + 2 * cx;
+    __nv_bfloat16* const ph = pk + (size_t)((((unsigned)b * C8 + (q >> 1)) * S32 + s00 + odd) * 8u);
+    __nv_bfloat16* const pl = ph + plane;
+    float* const po = out + (size_t)(((unsigned)b * S32 + s00) * (unsigned)C + q * 4);
 #pragma unroll
     for (int dz = 0; dz < 2; ++dz) {
 #pragma unroll
@@ -850,11 +887,10 @@ __global__ void __launch_bounds__(256, 2) upsample2x_fwd_c27_k(const float* __re
         float4 r[2];
 #pragma unroll
         for (int dx = 0; dx < 2; ++dx)
-          r[dx] = dz == 0 ? lerp4(lz0, sel4(iz, P[0][dy][dx], P[1][dy][dx]), sel4(iz, P[1][dy][dx], P[2][dy][dx]))
-                          : lerp4(0.25f, P[1][dy][dx], P[2][dy][dx]);
-        const size_t s = ((size_t)(2 * cz + dz) * H + (2 * cy + dy)) * W + 2 * cx;
+          r[dx] = dz == 0 ? lerp4(lz0, P[0][dy][dx], P[1][dy][dx]) : lerp4(0.25f, P[1][dy][dx], P[2][dy][dx]);
+        const unsigned ds = ((unsigned)dz * H + dy) * W;   // fine-voxel offset of this (dz, dy) row
         if (out && valid) {
-          float* o = out + ((size_t)b * S + s) * C + q * 4;
+          float* o = po + ds * (unsigned)C;
           *reinterpret_cast<float4*>(o) = r[0];
           *reinterpret_cast<float4*>(o + C) = r[1];
         }
@@ -862,11 +898,13 @@ __global__ void __launch_bounds__(256, 2) upsample2x_fwd_c27_k(const float* __re
           uint2 hi[2], lo[2];
 #pragma unroll
           for (int dx = 0; dx < 2; ++dx) {
-            __nv_bfloat16 hh[4], ll[4];
-            split_bf16(r[dx].x, hh[0], ll[0]); split_bf16(r[dx].y, hh[1], ll[1]);
-            split_bf16(r[dx].z, hh[2], ll[2]); split_bf16(r[dx].w, hh[3], ll[3]);
-            hi[dx] = pack4_bf16(hh[0], hh[1], hh[2], hh[3]);
-            lo[dx] = pack4_bf16(ll[0], ll[1], ll[2], ll[3]);
+            // split x = hi + lo two channels at a time (same roundings as split_bf16)
+            const __nv_bfloat162 h01 = __floats2bfloat162_rn(r[dx].x, r[dx].y), h23 = __floats2bfloat162_rn(r[dx].z, r[dx].w);
+            const float2 f01 = __bfloat1622float2(h01), f23 = __bfloat1622float2(h23);
+            const __nv_bfloat162 l01 = __floats2bfloat162_rn(r[dx].x - f01.x, r[dx].y - f01.y);
+            const __nv_bfloat162 l23 = __floats2bfloat162_rn(r[dx].z - f23.x, r[dx].w - f23.y);
+            hi[dx] = make_uint2(*reinterpret_cast<const uint32_t*>(&h01), *reinterpret_cast<const uint32_t*>(&h23));
+            lo[dx] = make_uint2(*reinterpret_cast<const uint32_t*>(&l01), *reinterpret_cast<const uint32_t*>(&l23));
           }
           // even quad keeps X = 2x (dx 0) and receives the partner's channels 4..7 of it; odd quad keeps X = 2x+1
           const uint2 sh = odd ? hi[0] : hi[1], sl = odd ? lo[0] : lo[1];
@@ -876,11 +914,10 @@ __global__ void __launch_bounds__(256, 2) upsample2x_fwd_c27_k(const float* __re
           if (valid) {
             const uint2 mh = odd ? hi[1] : hi[0], ml = odd ? lo[1] : lo[0];
             const uint4 vh = odd ? make_uint4(gh.x, gh.y, mh.x, mh.y) : make_uint4(mh.x, mh.y, gh.x, gh.y);
-            __nv_bfloat16* dst = pk + (((size_t)b * C8 + (q >> 1)) * S + s + odd) * 8;
-            *reinterpret_cast<uint4*>(dst) = vh;
+            *reinterpret_cast<uint4*>(ph + ds * 8u) = vh;
             if (write_lo) {
               const uint4 vl = odd ? make_uint4(gl.x, gl.y, ml.x, ml.y) : make_uint4(ml.x, ml.y, gl.x, gl.y);
-              *reinterpret_cast<uint4*>(dst + plane) = vl;
+              *reinterpret_cast<uint4*>(pl + ds * 8u) = vl;
             }
           }
         }
@@ -892,7 +929,7 @@ ICL_API int icl_upsample2x_fwd(const float* x, float* out, void* pk, int write_l
   ICL_REQUIRE(pk == nullptr || C % 8 == 0, "upsample2x: PK output needs C %% 8 == 0");
   ICL_REQUIRE(pk != nullptr || out != nullptr, "upsample2x: no output requested");
   const int C8u = C / 8;
-  if (C % 8 == 0 && (long long)B * d * h * w * (C / 4) < (1LL << 31)) {
+  if (C % 8 == 0 && 8LL * B * d * h * w * C < (1LL << 31)) {
     const long long threads = (long long)B * d * h * w * (C / 4);
     upsample2x_fwd_c27_k<<<grid_for(threads, 256, 148 * 32), 256, 0, as_stream(stream)>>>(x, out, (__nv_bfloat16*)pk, write_lo, B, C, d, h, w);
     ICL_LAUNCHED("upsample2x_fwd");
@@ -997,39 +1034,57 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_v4_k(const float* __restri
 __global__ void __launch_bounds__(256) upsample2x_bwd_sep_k(const float* __restrict__ dout, int Cd, int c_off, float* __restrict__ dx,
                                                             int accumulate, int B, int C, int d, int h, int w) {
   const int D = 2 * d, H = 2 * h, W = 2 * w, C4 = C >> 2;
-  const unsigned total = (unsigned)B * d * h * w * C4;   // host guarantees < 2^31
-  for (unsigned i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c = (int)(i % (unsigned)C4) * 4;
-    unsigned v = i / (unsigned)C4;
-    const int x = (int)(v % (unsigned)w); v /= (unsigned)w;
-    const int y = (int)(v % (unsigned)h); v /= (unsigned)h;
-    const int z = (int)(v % (unsigned)d);
-    const int b = (int)(v / (unsigned)d);
-    float wz[4], wy[4], wx[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      wz[k] = up2_wt(2 * z - 1 + k, d, z);
-      wy[k] = up2_wt(2 * y - 1 + k, h, y);
-      wx[k] = up2_wt(2 * x - 1 + k, w, x);
-    }
+  {
+    const Up2Tile t = up2_tile(C4, d, h, w);
+    if (!t.valid) return;
+    const int c = t.q * 4, x = t.x, y = t.y, z = t.z, b = t.b;
     const float* base = dout + (size_t)b * D * H * W * Cd + c_off + c;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x > 0 && x < w - 1 && y > 0 && y < h - 1 && z > 0 && z < d - 1) {
+      // interior cell: the weights of fine offsets -1..2 are (.25, .75, .75, .25) on every axis (what up2_wt returns there)
+      const float* p0 = base + (((size_t)(2 * z - 1) * H + (2 * y - 1)) * W + (2 * x - 1)) * Cd;
+      const size_t rs = (size_t)W * Cd, ps = (size_t)H * W * Cd;
 #pragma unroll
-    for (int kz = 0; kz < 4; ++kz) {
-      if (wz[kz] == 0.f) continue;
+      for (int kz = 0; kz < 4; ++kz) {
 #pragma unroll
-      for (int ky = 0; ky < 4; ++ky) {
-        if (wy[ky] == 0.f) continue;
-        const float* row = base + ((size_t)(2 * z - 1 + kz) * H + (2 * y - 1 + ky)) * W * Cd;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int kx = 0; kx < 4; ++kx) {
-          if (wx[kx] == 0.f) continue;
-          const float4 g = *reinterpret_cast<const float4*>(row + (size_t)(2 * x - 1 + kx) * Cd);
-          t.x += wx[kx] * g.x; t.y += wx[kx] * g.y; t.z += wx[kx] * g.z; t.w += wx[kx] * g.w;
+        for (int ky = 0; ky < 4; ++ky) {
+          const float* row = p0 + kz * ps + ky * rs;
+          const float4 g0 = *reinterpret_cast<const float4*>(row), g1 = *reinterpret_cast<const float4*>(row + Cd);
+          const float4 g2 = *reinterpret_cast<const float4*>(row + 2 * Cd), g3 = *reinterpret_cast<const float4*>(row + 3 * Cd);
+          float4 t;   // same order of the adds as the general path below
+          t.x = 0.25f * g0.x; t.x += 0.75f * g1.x; t.x += 0.75f * g2.x; t.x += 0.25f * g3.x;
+          t.y = 0.25f * g0.y; t.y += 0.75f * g1.y; t.y += 0.75f * g2.y; t.y += 0.25f * g3.y;
+          t.z = 0.25f * g0.z; t.z += 0.75f * g1.z; t.z += 0.75f * g2.z; t.z += 0.25f * g3.z;
+          t.w = 0.25f * g0.w; t.w += 0.75f * g1.w; t.w += 0.75f * g2.w; t.w += 0.25f * g3.w;
+          const float wzy = ((kz == 0 || kz == 3) ? 0.25f : 0.75f) * ((ky == 0 || ky == 3) ? 0.25f : 0.75f);
+          acc.x += wzy * t.x; acc.y += wzy * t.y; acc.z += wzy * t.z; acc.w += wzy * t.w;
         }
-        const float wzy = wz[kz] * wy[ky];
-        acc.x += wzy * t.x; acc.y += wzy * t.y; acc.z += wzy * t.z; acc.w += wzy * t.w;
+      }
+    } else {
+      float wz[4], wy[4], wx[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        wz[k] = up2_wt(2 * z - 1 + k, d, z);
+        wy[k] = up2_wt(2 * y - 1 + k, h, y);
+        wx[k] = up2_wt(2 * x - 1 + k, w, x);
+      }
+#pragma unroll
+      for (int kz = 0; kz < 4; ++kz) {
+        if (wz[kz] == 0.f) continue;
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+          if (wy[ky] == 0.f) continue;
+          const float* row = base + ((size_t)(2 * z - 1 + kz) * H + (2 * y - 1 + ky)) * W * Cd;
+          float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int kx = 0; kx < 4; ++kx) {
+            if (wx[kx] == 0.f) continue;
+            const float4 g = *reinterpret_cast<const float4*>(row + (size_t)(2 * x - 1 + kx) * Cd);
+            t.x += wx[kx] * g.x; t.y += wx[kx] * g.y; t.z += wx[kx] * g.z; t.w += wx[kx] * g.w;
+          }
+          const float wzy = wz[kz] * wy[ky];
+          acc.x += wzy * t.x; acc.y += wzy * t.y; acc.z += wzy * t.z; acc.w += wzy * t.w;
+        }
       }
     }
     float4* o = reinterpret_cast<float4*>(dx + ((((size_t)b * d + z) * h + y) * w + x) * C + c);
@@ -1039,8 +1094,8 @@ __global__ void __launch_bounds__(256) upsample2x_bwd_sep_k(const float* __restr
 }
 ICL_API int icl_upsample2x_bwd(const float* dout, int Cd, int c_off, float* dx, int accumulate, int B, int C, int d, int h, int w,
                                void* stream) {
-  if (C % 4 == 0 && Cd % 4 == 0 && c_off % 4 == 0 && (long long)B * (C / 4) * d * h * w < (1LL << 31)) {
-    upsample2x_bwd_sep_k<<<grid_for((long long)B * (C / 4) * d * h * w, 256, 148 * 32), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate,
+  if (up2_tile_ok(C) && Cd % 4 == 0 && c_off % 4 == 0 && up2_tile_blocks(B, C / 4, d, h, w) < (1LL << 31)) {
+    upsample2x_bwd_sep_k<<<(unsigned)up2_tile_blocks(B, C / 4, d, h, w), 256, 0, as_stream(stream)>>>(dout, Cd, c_off, dx, accumulate,
                                                                                                                  B, C, d, h, w);
     ICL_LAUNCHED("upsample2x_bwd");
   }

@@ -9,6 +9,8 @@ table is uploaded from pinned memory.
     step = GraphedStep(lambda x, y: train_step(x, y), (x_example, y_example), optimizer)
     loss = step(x, y)          # copies x, y into the static buffers, refreshes the lr, replays; returns the static loss
 """
+import os
+
 import torch
 
 
@@ -24,7 +26,10 @@ class GraphedStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
+        # the step is captured on a high-priority stream: its kernels (the backbone chain) are scheduled ahead of the kernels of the
+        # side lanes forked from it (icl_b200/lanes.py), which run at the default priority
+        prio = int(os.environ.get("ICL_GRAPH_PRIORITY", "-1"))
+        with torch.cuda.graph(self.graph, stream=torch.cuda.Stream(priority=prio)):
             self.static_out = self.fn(*self.static_in)
         torch.cuda.synchronize()
 

@@ -23,14 +23,17 @@ def enabled(device):
     return device.type == "cuda" and os.environ.get("ICL_HEAD_LANES", "1") != "0"
 
 
-def get(device, names, priority=-1):
-    """{name: stream} of cached side streams on `device` (+ "main": the current stream).  priority -1: scheduled ahead of the caller's
-    stream (the heads' small kernels slip in between the backbone's large ones); 0: same as the caller's."""
+def get(device, names, priority=0):
+    """{name: stream} of cached side streams on `device` (+ "main": the current stream).  Lanes run at the default priority; the
+    captured step's own stream is created with a higher one (icl_b200/graph.py), so the backbone chain — the critical path — is
+    scheduled ahead of the lanes' kernels (measured: 12.19 ms vs 12.30 ms with the priorities the other way round)."""
     idx = device.index if device.index is not None else torch.cuda.current_device()
     out = {"main": torch.cuda.current_stream(device)}
     for n in names:
         s = _STREAMS.get((idx, n))
         if s is None:
+            if "ICL_LANE_PRIORITY" in os.environ:   # measurement knob
+                priority = int(os.environ["ICL_LANE_PRIORITY"])
             s = _STREAMS[(idx, n)] = torch.cuda.Stream(device=device, priority=priority)
         out[n] = s
     return out

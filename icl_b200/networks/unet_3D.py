@@ -83,7 +83,7 @@ class _Backbone3DModule(nn.Module):
         cfg = self._pair_cfg(x_lab, x_unlab)
         ps = self._backbone_params()
         st = _PairState()
-        o = BackbonePairLowFn.apply(torch.cat([x_lab, x_unlab]), x_lab.shape[0], cfg, st, [w.detach() for w in ps[N_LOW:N_LOW + 8:2]],
+        o = BackbonePairLowFn.apply(torch.cat([x_lab, x_unlab]), x_lab.shape[0], cfg, st, list(ps[N_LOW:N_LOW + 8:2]),
                                     *ps[:N_LOW])
         return (o[0], o[2], o[4]), (o[1], o[3], o[5]), (o[6], st, ps[N_LOW:])
 
