@@ -6,6 +6,7 @@
 //   * conv3d_wgrad      : weight (+bias) gradient, fp32 FFMA with register-tiled sliding window.
 // Reference semantics: nn.Conv3d(k=3, s=1, p=1, bias=True), networks/utils.py:104,107.
 #include "common.cuh"
+#include <stdlib.h>
 
 // ------------------------------------------------------------------------------------------
 // weight repacking:  torch [Cout][Cin][27]  ->  fwd  : wp[tap][ci][co]
@@ -331,11 +332,156 @@ __global__ void __launch_bounds__(256) conv3d_stem_fwd_k(const float* __restrict
     }
   }
 }
+// Persistent form of the kernel above (same tile, same per-thread arithmetic in the same order): two CTAs per SM walk the tiles, the
+// halo of the NEXT tile arrives by cp.async (zero-fill outside the volume) while the current one is computed, and the InstanceNorm
+// statistics are reduced across the warp with a 31-shuffle transposing reduction (lane l ends up with the warp total of value l:
+// 16 sums, 16 sums of squares) and accumulated in double precision in shared memory until the sample changes — the one-tile-per-CTA
+// kernel spent its time in the load / barrier / 160-shuffle phases around the FMA loop (ncu: 40 % issue utilisation, 29 % FMA pipe).
+__device__ __forceinline__ void cp_async4_zfill(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = ok ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__global__ void __launch_bounds__(256, 2) conv3d_stem_fwd2_k(const float* __restrict__ x, const float* __restrict__ w /* [16][1][27] */,
+                                                             const float* __restrict__ bias, float* __restrict__ y, double* __restrict__ stats,
+                                                             int B, int D, int H, int W, int tiles_total) {
+  __shared__ float xs[2][ST_HALO];
+  __shared__ __align__(16) float ws[27][ST_CO];
+  __shared__ double red[8][32];
+  __shared__ float bs[ST_CO];
+  const int tw = cdiv(W, ST_W), th = cdiv(H, ST_H), td = cdiv(D, ST_D);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  for (int i = tid; i < 27 * ST_CO; i += 256) ws[i % 27][i / 27] = w[i];  // w[co*27 + tap]
+  if (tid < ST_CO) bs[tid] = bias ? bias[tid] : 0.f;
+  red[wid][lane] = 0.0;
+  // this thread's halo slots (the same for every tile): slot k is element tid + 256 k of the [ST_D+2][ST_H+2][ST_HW] halo
+  int hpd[8], hph[8], hpw[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int i = tid + k * 256;
+    hpw[k] = i % ST_HW; hph[k] = (i / ST_HW) % (ST_H + 2); hpd[k] = i / (ST_HW * (ST_H + 2));
+  }
+  auto prefetch = [&](int tile, int buf) {
+    int t = tile;
+    const int bw = t % tw; t /= tw;
+    const int bh = t % th; t /= th;
+    const int bd = t % td;
+    const int b = t / td;
+    const float* xb = x + (long long)b * D * H * W;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int i = tid + k * 256;
+      if (i < ST_HALO) {
+        const int gd = bd * ST_D + hpd[k] - 1, gh = bh * ST_H + hph[k] - 1, gw = bw * ST_W + hpw[k] - 1;
+        const bool ok = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
+        cp_async4_zfill(&xs[buf][i], ok ? xb + ((long long)gd * H + gh) * W + gw : x, ok);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto flush = [&](int b) {   // block-uniform call
+    __syncthreads();
+    if (tid < 32) {
+      double tsum = 0.0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tsum += red[k][tid];
+      atomicAdd(&stats[((long long)b * ST_CO + (tid & 15)) * 2 + (tid >> 4)], tsum);
+    }
+    __syncthreads();
+    red[wid][lane] = 0.0;
+  };
+  const int lw = (tid % 8) * 4, lh = (tid / 8) % ST_H, ld = tid / (8 * ST_H);
+  int buf = 0, cur_b = -1;
+  if ((int)blockIdx.x < tiles_total) prefetch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < tiles_total) prefetch(next, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    int t = tile;
+    const int bw = t % tw; t /= tw;
+    const int bh = t % th; t /= th;
+    const int bd = t % td;
+    const int b = t / td;
+    if (b != cur_b) {
+      if (cur_b >= 0 && stats) flush(cur_b);
+      cur_b = b;
+    }
+    float acc[4][ST_CO];
+#pragma unroll
+    for (int v = 0; v < 4; ++v)
+#pragma unroll
+      for (int c = 0; c < ST_CO; ++c) acc[v][c] = 0.f;
+#pragma unroll
+    for (int k9 = 0; k9 < 9; ++k9) {
+      const float* row = &xs[buf][((ld + k9 / 3) * (ST_H + 2) + lh + k9 % 3) * ST_HW + lw];
+      float xv[6];
+#pragma unroll
+      for (int i = 0; i < 6; ++i) xv[i] = row[i];
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const float4* wv = reinterpret_cast<const float4*>(&ws[k9 * 3 + kw][0]);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 w4 = wv[q];
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            acc[v][q * 4 + 0] = fmaf(xv[v + kw], w4.x, acc[v][q * 4 + 0]);
+            acc[v][q * 4 + 1] = fmaf(xv[v + kw], w4.y, acc[v][q * 4 + 1]);
+            acc[v][q * 4 + 2] = fmaf(xv[v + kw], w4.z, acc[v][q * 4 + 2]);
+            acc[v][q * 4 + 3] = fmaf(xv[v + kw], w4.w, acc[v][q * 4 + 3]);
+          }
+        }
+      }
+    }
+    const int d = bd * ST_D + ld, h = bh * ST_H + lh, w0 = bw * ST_W + lw;
+    float sv[2 * ST_CO];
+#pragma unroll
+    for (int c = 0; c < 2 * ST_CO; ++c) sv[c] = 0.f;
+    const bool rowok = d < D && h < H;
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+      if (rowok && w0 + v < W) {
+        float* dst = y + ((((long long)b * D + d) * H + h) * W + w0 + v) * ST_CO;
+#pragma unroll
+        for (int c = 0; c < ST_CO; ++c) {
+          acc[v][c] += bs[c];
+          sv[c] += acc[v][c]; sv[ST_CO + c] += acc[v][c] * acc[v][c];
+        }
+#pragma unroll
+        for (int c = 0; c < ST_CO; c += 4) *reinterpret_cast<float4*>(dst + c) = make_float4(acc[v][c], acc[v][c + 1], acc[v][c + 2], acc[v][c + 3]);
+      }
+    }
+    if (stats) {
+      // transposing reduction: after the step with offset o, slot j of a lane holds value j + (lane & (32 - o)) summed over the
+      // lanes that differ from it in bits >= o; 16 + 8 + 4 + 2 + 1 shuffles leave the warp total of value `lane` in slot 0
+#pragma unroll
+      for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < off; ++j) {
+          const float send = up ? sv[j] : sv[j + off];
+          const float keep = up ? sv[j + off] : sv[j];
+          sv[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+        }
+      }
+      red[wid][lane] += (double)sv[0];
+    }
+    __syncthreads();   // every warp is done with xs[buf] before the next iteration's prefetch overwrites it
+  }
+  if (cur_b >= 0 && stats) flush(cur_b);
+}
 ICL_API int icl_conv3d_stem_fwd(const float* x, const float* w, const float* bias, float* y, double* stats, int B, int D, int H, int W, int Cout,
                                 void* stream) {
   ICL_REQUIRE(Cout == ST_CO, "conv3d_stem_fwd: Cout=%d (only 16 is built)", Cout);
   const long long tiles = (long long)B * cdiv(D, ST_D) * cdiv(H, ST_H) * cdiv(W, ST_W);
   ICL_REQUIRE(tiles < 2147483647LL, "conv3d_stem_fwd: too many tiles");
+  if (getenv("ICL_STEM_V1") == nullptr) {
+    const int grid = (int)min(tiles, (long long)148 * 2);
+    conv3d_stem_fwd2_k<<<grid, 256, 0, as_stream(stream)>>>(x, w, bias, y, stats, B, D, H, W, (int)tiles);
+    ICL_LAUNCHED("conv3d_stem_fwd");
+  }
   conv3d_stem_fwd_k<<<(unsigned)tiles, 256, 0, as_stream(stream)>>>(x, w, bias, y, stats, B, D, H, W);
   ICL_LAUNCHED("conv3d_stem_fwd");
 }
@@ -399,11 +545,98 @@ __global__ void __launch_bounds__(128) conv3d_stem_wgrad_k(const float* __restri
       for (int c = 0; c < 4; ++c) atomicAdd(dw + (co4 * 4 + c) * 27 + k9 * 3 + kw, acc[kw][c]);
   }
 }
+// The same kernel with the NEXT tile's operands (x halo, dy tile) arriving by cp.async into a second buffer while the current tile is
+// accumulated (the synchronous loads left the FMA pipe idle two thirds of the time: ncu 33 % FMA, 21 % warps active).
+#define SW2_BUF_FLOATS (SW_HALO + SW_D * ST_H * ST_W * ST_CO)
+__device__ __forceinline__ void cp_async16_zfill(float* dst, const float* src, bool ok) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  const int n = ok ? 16 : 0;
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(n) : "memory");
+}
+__global__ void __launch_bounds__(128) conv3d_stem_wgrad2_k(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
+                                                            int B, int D, int H, int W, int tiles_total) {
+  extern __shared__ __align__(16) float sw2[];   // [2][ ds: SW_D*ST_H*ST_W x 16 | xs: SW_HALO ]
+  const int tid = threadIdx.x;
+  const int co4 = tid % 4, k9 = (tid / 4) % 9, part = tid / 36;  // part 3 (threads 108..127) only helps staging
+  const int tw = cdiv(W, ST_W), th = cdiv(H, ST_H), td = cdiv(D, SW_D);
+  float acc[3][4];
+#pragma unroll
+  for (int i = 0; i < 3; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  auto prefetch = [&](int tile, int buf) {
+    float* ds = sw2 + (size_t)buf * SW2_BUF_FLOATS;
+    float* xs = ds + SW_D * ST_H * ST_W * ST_CO;
+    int t = tile;
+    const int bw = t % tw; t /= tw;
+    const int bh = t % th; t /= th;
+    const int bd = t % td;
+    const int b = t / td;
+    for (int i = tid; i < SW_HALO; i += 128) {
+      const int pw = i % ST_HW, ph = (i / ST_HW) % (ST_H + 2), pd = i / (ST_HW * (ST_H + 2));
+      const int gd = bd * SW_D + pd - 1, gh = bh * ST_H + ph - 1, gw = bw * ST_W + pw - 1;
+      const bool ok = gd >= 0 && gd < D && gh >= 0 && gh < H && gw >= 0 && gw < W;
+      cp_async4_zfill(&xs[i], ok ? x + (((long long)b * D + gd) * H + gh) * W + gw : x, ok);
+    }
+    for (int i = tid; i < SW_D * ST_H * ST_W * 4; i += 128) {
+      const int q = i % 4, pos = i / 4;
+      const int pw = pos % ST_W, ph = (pos / ST_W) % ST_H, pd = pos / (ST_W * ST_H);
+      const int gd = bd * SW_D + pd, gh = bh * ST_H + ph, gw = bw * ST_W + pw;
+      const bool ok = gd < D && gh < H && gw < W;
+      cp_async16_zfill(&ds[pos * ST_CO + q * 4], ok ? dy + ((((long long)b * D + gd) * H + gh) * W + gw) * ST_CO + q * 4 : dy, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int buf = 0;
+  if ((int)blockIdx.x < tiles_total) prefetch(blockIdx.x, 0);
+  for (int tile = blockIdx.x; tile < tiles_total; tile += gridDim.x, buf ^= 1) {
+    const int next = tile + gridDim.x;
+    if (next < tiles_total) prefetch(next, buf ^ 1);
+    else asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncthreads();
+    const float* ds = sw2 + (size_t)buf * SW2_BUF_FLOATS;
+    const float* xs = ds + SW_D * ST_H * ST_W * ST_CO;
+    if (part < 3) {
+      for (int row = part; row < SW_D * ST_H; row += 3) {
+        const int ld = row / ST_H, lh = row % ST_H;
+        const float* xr = &xs[((ld + k9 / 3) * (ST_H + 2) + lh + k9 % 3) * ST_HW];
+        float x0 = xr[0], x1 = xr[1];
+#pragma unroll 4
+        for (int lw = 0; lw < ST_W; ++lw) {
+          const float x2 = xr[lw + 2];
+          const float4 g = *reinterpret_cast<const float4*>(&ds[(row * ST_W + lw) * ST_CO + co4 * 4]);
+          acc[0][0] = fmaf(x0, g.x, acc[0][0]); acc[0][1] = fmaf(x0, g.y, acc[0][1]); acc[0][2] = fmaf(x0, g.z, acc[0][2]); acc[0][3] = fmaf(x0, g.w, acc[0][3]);
+          acc[1][0] = fmaf(x1, g.x, acc[1][0]); acc[1][1] = fmaf(x1, g.y, acc[1][1]); acc[1][2] = fmaf(x1, g.z, acc[1][2]); acc[1][3] = fmaf(x1, g.w, acc[1][3]);
+          acc[2][0] = fmaf(x2, g.x, acc[2][0]); acc[2][1] = fmaf(x2, g.y, acc[2][1]); acc[2][2] = fmaf(x2, g.z, acc[2][2]); acc[2][3] = fmaf(x2, g.w, acc[2][3]);
+          x0 = x1; x1 = x2;
+        }
+      }
+    }
+    __syncthreads();   // done with this buffer before the next iteration's prefetch refills it
+  }
+  if (part < 3) {
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) atomicAdd(dw + (co4 * 4 + c) * 27 + k9 * 3 + kw, acc[kw][c]);
+  }
+}
 ICL_API int icl_conv3d_stem_wgrad(const float* x, const float* dy, float* dw /* zeroed [16][1][27] */, int B, int D, int H, int W, int Cout,
                                   void* stream) {
   ICL_REQUIRE(Cout == ST_CO, "conv3d_stem_wgrad: Cout=%d (only 16 is built)", Cout);
   const long long tiles = (long long)B * cdiv(D, SW_D) * cdiv(H, ST_H) * cdiv(W, ST_W);
   ICL_REQUIRE(tiles < 2147483647LL, "conv3d_stem_wgrad: too many tiles");
+  if (getenv("ICL_STEM_V1") == nullptr) {
+    const size_t smem = 2 * (size_t)SW2_BUF_FLOATS * sizeof(float);
+    static bool attr_done = false;
+    if (!attr_done) {
+      ICL_REQUIRE(cudaFuncSetAttribute(conv3d_stem_wgrad2_k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) == cudaSuccess,
+                  "conv3d_stem_wgrad: cannot raise the dynamic shared-memory limit");
+      attr_done = true;
+    }
+    const int grid = (int)min(tiles, (long long)148 * 2);
+    conv3d_stem_wgrad2_k<<<grid, 128, smem, as_stream(stream)>>>(x, dy, dw, B, D, H, W, (int)tiles);
+    ICL_LAUNCHED("conv3d_stem_wgrad");
+  }
   const int grid = (int)min(tiles, (long long)148 * 4);
   conv3d_stem_wgrad_k<<<grid, 128, 0, as_stream(stream)>>>(x, dy, dw, B, D, H, W, (int)tiles);
   ICL_LAUNCHED("conv3d_stem_wgrad");

@@ -71,3 +71,22 @@ def join_all(device=None):
                 if not torch.cuda.is_current_stream_capturing():
                     continue
         cur.wait_stream(s)
+
+
+def fan(device, prefix, thunks, tensors=()):
+    """Runs the independent thunks on lanes prefix0, prefix1, ... forked from the current stream and joins them: [results].
+    `tensors`: inputs produced elsewhere that the thunks read (announced to the allocator per lane).  Results that are tensors (or
+    tuples of tensors) are announced for the current stream.  Sequential without lanes or with a single thunk."""
+    if len(thunks) < 2 or not enabled(device):
+        return [t() for t in thunks]
+    L = get(device, ["%s%d" % (prefix, i) for i in range(len(thunks))])
+    main = L["main"]
+    out = []
+    for i, t in enumerate(thunks):
+        lane = L["%s%d" % (prefix, i)]
+        handoff(lane, main, *tensors)
+        with on(lane):
+            r = t()
+        out.append(r)
+        handoff(main, lane, *(r if isinstance(r, (tuple, list)) else (r,)))
+    return out

@@ -9,7 +9,7 @@ No .item() host syncs (the reference's DiceLoss does K of them per call, utils/l
 import torch
 import torch.nn as nn
 
-from .. import ops
+from .. import lanes, ops
 from ..ops import P, c_d, c_f, c_int, c_ll, call
 
 
@@ -125,8 +125,10 @@ class AuxLoss3D(nn.Module):
 
     def forward(self, feat_maps, labels):
         ce_sum, dice_sum = None, None
-        for fm in feat_maps:
-            ce, dc = seg_ce_dice(fm, labels, self.resize)
+        # the scales are independent: one lane each (icl_b200/lanes.py), summed in the reference's order after the join
+        res = lanes.fan(labels.device, "loss", [lambda fm=fm: seg_ce_dice(fm, labels, self.resize) for fm in feat_maps],
+                        list(feat_maps) + [labels])
+        for ce, dc in res:
             ce_sum = ce if ce_sum is None else ce_sum + ce
             dice_sum = dc if dice_sum is None else dice_sum + dc
         n = len(feat_maps)
@@ -143,8 +145,7 @@ class PseudoSoftLoss3D(nn.Module):
     def forward(self, feat_maps, predicts):
         tgt = predicts.detach()
         tot = None
-        for fm in feat_maps:
-            d = soft_dice(fm, tgt, self.resize)
+        for d in lanes.fan(tgt.device, "loss", [lambda fm=fm: soft_dice(fm, tgt, self.resize) for fm in feat_maps], list(feat_maps) + [tgt]):
             tot = d if tot is None else tot + d
         return tot / len(feat_maps)
 
@@ -195,8 +196,10 @@ def softmax_mse_loss(input_logits, target_logits, sigmoid=False):
     if sigmoid:
         raise NotImplementedError("icl_b200 softmax_mse_loss implements the sigmoid=False branch the ICL loops use")
     tot = None
-    for a, b in zip(input_logits, target_logits):
-        m = _SoftmaxMseFn.apply(a, b.detach())
+    pairs = list(zip(input_logits, target_logits))
+    dev = pairs[0][0].device if pairs else torch.device("cpu")
+    for m in lanes.fan(dev, "loss", [lambda a=a, b=b: _SoftmaxMseFn.apply(a, b.detach()) for a, b in pairs],
+                       [t for ab in pairs for t in ab]):
         tot = m if tot is None else tot + m
     return tot / len(input_logits)
 

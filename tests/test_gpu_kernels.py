@@ -62,7 +62,7 @@ def test_conv3d_direct_dgrad_and_wgrad():
     assert_close(db.cpu(), b.grad, 1e-5, "bgrad")
 
 
-@pytest.mark.parametrize("B,dims", [(2, (8, 16, 32)), (1, (6, 12, 40)), (1, (4, 9, 33))])
+@pytest.mark.parametrize("B,dims", [(2, (8, 16, 32)), (1, (6, 12, 40)), (1, (4, 9, 33)), (2, (32, 64, 96))])   # last: more tiles than CTAs
 def test_conv3d_stem_fwd_and_wgrad(B, dims):
     """Cin=1 -> 16 stem specialisations vs F.conv3d and its autograd."""
     ops = _ops()
