@@ -13,6 +13,15 @@ from .. import lanes, ops
 from ..ops import P, c_d, c_f, c_int, c_ll, call
 
 
+def _fan(K, device, thunks, tensors):
+    """The scales of a multi-scale loss are independent: with many classes (K >= 8: every scale streams >100 MB at 96^3 and one
+    kernel alone reaches a third of the HBM bandwidth) each runs on a lane of its own (icl_b200/lanes.py), summed in the reference's
+    order after the join.  With few classes the kernels are 25-35 us and the fork / join costs what it saves (measured, config 2)."""
+    if K < 8:
+        return [t() for t in thunks]
+    return lanes.fan(device, "loss", thunks, tensors)
+
+
 def _layout(src):
     """Returns (tensor, planar flag): channels-last 5-D tensors are consumed in place, anything else as planar.
     4-D [B,K,H,W] inputs (the 2D path) are handled as depth-1 volumes."""
@@ -125,9 +134,8 @@ class AuxLoss3D(nn.Module):
 
     def forward(self, feat_maps, labels):
         ce_sum, dice_sum = None, None
-        # the scales are independent: one lane each (icl_b200/lanes.py), summed in the reference's order after the join
-        res = lanes.fan(labels.device, "loss", [lambda fm=fm: seg_ce_dice(fm, labels, self.resize) for fm in feat_maps],
-                        list(feat_maps) + [labels])
+        res = _fan(feat_maps[0].shape[1], labels.device, [lambda fm=fm: seg_ce_dice(fm, labels, self.resize) for fm in feat_maps],
+                   list(feat_maps) + [labels])
         for ce, dc in res:
             ce_sum = ce if ce_sum is None else ce_sum + ce
             dice_sum = dc if dice_sum is None else dice_sum + dc
@@ -145,7 +153,7 @@ class PseudoSoftLoss3D(nn.Module):
     def forward(self, feat_maps, predicts):
         tgt = predicts.detach()
         tot = None
-        for d in lanes.fan(tgt.device, "loss", [lambda fm=fm: soft_dice(fm, tgt, self.resize) for fm in feat_maps], list(feat_maps) + [tgt]):
+        for d in _fan(tgt.shape[1], tgt.device, [lambda fm=fm: soft_dice(fm, tgt, self.resize) for fm in feat_maps], list(feat_maps) + [tgt]):
             tot = d if tot is None else tot + d
         return tot / len(feat_maps)
 
@@ -198,8 +206,8 @@ def softmax_mse_loss(input_logits, target_logits, sigmoid=False):
     tot = None
     pairs = list(zip(input_logits, target_logits))
     dev = pairs[0][0].device if pairs else torch.device("cpu")
-    for m in lanes.fan(dev, "loss", [lambda a=a, b=b: _SoftmaxMseFn.apply(a, b.detach()) for a, b in pairs],
-                       [t for ab in pairs for t in ab]):
+    for m in _fan(pairs[0][0].shape[1] if pairs else 0, dev, [lambda a=a, b=b: _SoftmaxMseFn.apply(a, b.detach()) for a, b in pairs],
+                  [t for ab in pairs for t in ab]):
         tot = m if tot is None else tot + m
     return tot / len(input_logits)
 
