@@ -575,7 +575,7 @@ def measure_train(a, wl, rank, world, dev, local, full=True):
                 if ent:
                     top = dict(ent, share=gk["share"], graph_kernel=gk["kernel"], graph_us_per_launch=gk["us_per_launch"])
                     break
-        line["roofline"] = roofline_of(top, pk)
+        line["roofline"] = roofline_of(top, pk, 3.0 if a.precision == "parity" else 1.0)
     return line
 
 
@@ -617,16 +617,21 @@ def cupti_kernel_times(step, n):
             for k, (us, c) in sorted(agg.items(), key=lambda kv: -kv[1][0])]
 
 
-def roofline_of(top, pk):
+def roofline_of(top, pk, mma_mult=3.0):
     # dominant kernel = largest share of the step's device time (CUDA events around every launch of our kernels in an eager pass of
     # the same step, on the launching stream); achieved = algorithmic FLOPs or bytes / that time
-    bound = "tensor" if top["name"].startswith("icl_conv3d") else "hbm"
+    # a kernel with both an algorithmic byte and FLOP count (the fused rank-R mlp2 update: HBM-bound for R <= 256, tensor-bound for
+    # the R >= 512 of data-parallel runs) is measured against the resource it uses the larger fraction of (MMAs ISSUED: x mma_mult)
+    tf = top["gflop_per_launch"] / top["ms_per_launch"] if top.get("gflop_per_launch") else 0.0
+    gb = top["mbytes_per_launch"] / top["ms_per_launch"] if top.get("mbytes_per_launch") else 0.0
+    bound = "tensor" if top["name"].startswith("icl_conv3d") or (mma_mult * tf / pk["tf_sus"] > gb / pk["hbm"]) else "hbm"
     if bound == "tensor":
-        ach, peak, unit = top["gflop_per_launch"] / top["ms_per_launch"], pk["tf_sus"], "TFLOP/s"
+        ach, peak, unit = tf, pk["tf_sus"], "TFLOP/s"
     else:
-        ach, peak, unit = top["mbytes_per_launch"] / top["ms_per_launch"], pk["hbm"], "GB/s"
+        ach, peak, unit = gb, pk["hbm"], "GB/s"
     traffic = None
-    for tname in ("traffic_r02.json", "traffic_r01.json"):
+    # (the DRAM capture of the fused update is the R = 32 one: not attached when the kernel runs tensor-bound at another R)
+    for tname in (("traffic_r02.json", "traffic_r01.json") if bound == "hbm" or top["name"].startswith("icl_conv3d") else ()):
         tpath = os.path.join(ROOT, "profiles", tname)
         if os.path.exists(tpath):
             ent = json.load(open(tpath)).get(top["name"])
@@ -637,6 +642,9 @@ def roofline_of(top, pk):
     out = {"kernel": top["name"], "bound": bound, "achieved": ach, "peak": peak, "unit": unit, "frac": ach / peak if peak else None,
            "traffic": traffic, "peak_source": pk["src"] + " (sustained)", "share_of_step": top["share"],
            "launches_per_step": top["launches_per_step"], "ms_per_launch_cuda_events": top["ms_per_launch"]}
+    if bound == "tensor":
+        out["mma_issue_frac"] = mma_mult * ach / peak if peak else None
+        out["note"] = "achieved = algorithmic TFLOP/s; the parity mode issues %g MMAs per algorithmic MMA (mma_issue_frac)" % mma_mult
     if "graph_kernel" in top:
         out["selected_by"] = "largest share of the replayed step's kernel time (CUPTI records): %s, %.1f us per launch in the graph" % (
             top["graph_kernel"], top["graph_us_per_launch"])
