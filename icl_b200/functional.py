@@ -5,6 +5,8 @@ InherentConsistent / Class_Decoder / Query_Attention / SeparableConv3d (networks
 Autograd composes them, so the reference's gradient pruning (dead uscl branches, detached targets) and its
 `.grad is None` set fall out of the graph structure exactly as they do for the reference.
 """
+import os
+
 import torch
 
 from . import ops, parallel
@@ -52,10 +54,15 @@ class LinearFn(torch.autograd.Function):
                     # the event lets the optimizer start this weight's update as soon as its last factor pair exists (optim.SGD
                     # may run the update on a lane of its own, next to the rest of backward)
                     ev = None
+                    sim = int(os.environ.get("ICL_SIM_RANKS", "1"))
+                    if sim > 1:
+                        # measurement knob: the compute load of `sim` data-parallel ranks on one GPU — the factor rows repeated `sim`
+                        # times with weight 1/sim (the mean over `sim` identical ranks: the same gradient, sim-fold rank)
+                        g, x2 = g.repeat(sim, 1), x2.repeat(sim, 1)
                     if g.is_cuda:
                         ev = torch.cuda.Event()
                         ev.record()
-                    sink.append((g, x2, 1.0, ev, None))
+                    sink.append((g, x2, 1.0 / sim, ev, None))
                 if ctx.has_bias:
                     db = torch.empty((w_.shape[0],), dtype=torch.float32, device=g.device)
                     call("icl_colsum", P(g), P(db), c_ll(g.shape[0]), c_int(w_.shape[0]), c_int(0))

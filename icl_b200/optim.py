@@ -59,8 +59,8 @@ class SGD(torch.optim.Optimizer):
         """The updates run on a lane of their own that waits only for the factors (events recorded where backward produced them):
         inside a captured step the HBM-bound updates then run next to the tensor-core-bound backbone backward instead of after it
         (config 2: 13.4 -> 12.7 ms per step).  While the update is HBM-bound (R <= 256) it gets 64 persistent CTAs, which still pull
-        most of the bandwidth and leave the other SMs to the convolutions; tensor-bound updates (large R: data parallel) keep one CTA
-        per SM.  ICL_OPT_LANE=0 disables the lane, ICL_OPT_CTAS overrides the CTA count.  Eager steps are enqueued in program order
+        most of the bandwidth and leave the other SMs to the convolutions; tensor-bound updates (large R: data parallel) get 96
+        (config 3 with the factor rows of 8 ranks, ICL_SIM_RANKS=8: 19.6 ms with 148 CTAs, 19.0 with 96, 20.0 with 64).  ICL_OPT_LANE=0 disables the lane, ICL_OPT_CTAS overrides the CTA count.  Eager steps are enqueued in program order
         either way."""
         lane = main = None
         ctas_env = -1
@@ -91,7 +91,7 @@ class SGD(torch.optim.Optimizer):
                     f[1].record_stream(lane)
             ctas = 0
             if lane is not None:
-                ctas = ctas_env if ctas_env >= 0 else (64 if sum(f[0].shape[0] for f in fs) <= 256 else 0)
+                ctas = ctas_env if ctas_env >= 0 else (64 if sum(f[0].shape[0] for f in fs) <= 256 else 96)
             with lanes.on(lane):
                 ops.sgd_factored(p, st["momentum_buffer"], [(f[0], f[1], f[2] if len(f) > 2 else 1.0) for f in fs], lr, group["momentum"],
                                  group["weight_decay"], max_ctas=ctas)
